@@ -1,0 +1,156 @@
+/* vpt_b200.h -- C ABI of the B200-native VPT policy forward path (libvpt_b200.so).
+ *
+ * The reference (openai/Video-Pre-Training) is pure Python on top of torch (it has NO FFI of its own, SURVEY.md
+ * section 2.1), so each entry point below replaces the torch / ATen call sequence of one reference site; the
+ * reference file:line each one stands in for is cited.  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns every buffer, including workspaces; entry points never allocate device memory, never
+ *     synchronise, and enqueue on the given `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, <0 on error; vpt_last_error() returns a thread-local message;
+ *   - bf16 tensors are row-major with the channel / feature dimension contiguous (NHWC for images).
+ *
+ * "row group statistics": several ops take `mr` = float[G][2] = (mean, rstd) of row group g = row / rows_per_group
+ * (a frame for GroupNorm(1 group), one token for LayerNorm) and several ops emit `stat_part` = partial
+ * (sum, sum of squares) of the values they stored; vpt_stats_finalize turns partials into `mr`.
+ */
+#ifndef VPT_B200_H_
+#define VPT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPT_OK 0
+#define VPT_ERR_ARG (-1)    /* bad argument / unsupported shape */
+#define VPT_ERR_CUDA (-2)   /* a CUDA runtime / driver call failed */
+#define VPT_ERR_DEVICE (-3) /* a kernel recorded a device-side protocol error (watchdog) */
+
+#define VPT_ABI_VERSION 1
+
+const char* vpt_last_error(void);
+int vpt_abi_version(void);
+/* Reads and clears the device-side watchdog flag (synchronises the device; for tests / debugging only). */
+int vpt_device_error(void);
+/* Number of SMs of the current device (grid sizing of the persistent kernels). */
+int vpt_num_sms(void);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM / implicit-GEMM 3x3 convolution (tcgen05.mma, TMA-fed, TMEM accumulators).
+ *
+ *   acc[m][n] = sum_k A[m][k] * B[n][k]                      (bf16 x bf16 -> fp32)
+ *   v = a_g * acc - b_g * S1[cls(m)][n] + S2[cls(m)][n]      (a_g,b_g) = (rstd_g, rstd_g*mean_g), or (1,0) if mr==NULL
+ *   relu==1: v = max(v,0);  v += residual[m][n];  relu==2: v = max(v,0);  v *= out_scale;  store
+ *
+ * With conv=0 this is  [LayerNorm ->] Linear [-> ReLU] [+ residual]  of lib/util.py:75-82 (linear flavour),
+ * lib/xf.py:336-338,355 (q/k/v/proj), lib/action_head.py:165 and lib/scaled_mse_head.py:35: the LayerNorm is folded
+ * (B pre-scaled by gamma; S1[n] = sum_k B[n][k]; S2[n] = sum_k W[n][k]*beta[k] (+ bias[n])).
+ * With conv=1 it is  GroupNorm(1) -> Conv2d 3x3 pad 1 -> ReLU [+ residual]  of lib/util.py:75-82 (conv flavour) and
+ * lib/impala_cnn.py:50-52: A is the raw NHWC activation tensor [F][H][W][Cin], k = tap*Cin + c, and cls(m) is the
+ * border class (row class * 3 + column class, 0 = first, 1 = interior, 2 = last) of output pixel m because the
+ * reference zero-pads AFTER normalising.
+ * -------------------------------------------------------------------------------------------------------- */
+typedef struct vpt_gemm_args {
+    const void* A;            /* bf16 */
+    const void* B;            /* bf16 [N][K], K contiguous */
+    int32_t M, N, K;          /* conv: M = F*H*W, K = 9*Cin */
+    int32_t conv;             /* 0 = linear, 1 = 3x3 pad-1 stride-1 convolution */
+    int32_t H, W, Cin;        /* conv geometry; Cin % 64 == 0; W*rows == 128 or H*W divides 128 */
+    const float* mr;          /* [G][2] (mean, rstd) or NULL */
+    int32_t rows_per_group;   /* rows (pixels) per statistics group */
+    const float* S1;          /* [ncls][N] (ncls = 9 for conv, 1 for linear) or NULL */
+    const float* S2;          /* [ncls][N] or NULL */
+    int32_t relu;             /* 0 none, 1 before the residual add, 2 after it */
+    float out_scale;
+    const void* residual;     /* [M][ld_res] or NULL */
+    int32_t residual_f32;     /* 0 = bf16, 1 = fp32 */
+    int64_t ld_res;
+    void* out;                /* [rows][ld_out] */
+    int32_t out_f32;
+    int64_t ld_out;
+    int32_t seg_len;          /* 0: out row = m; else out row = (m / seg_len) * seg_stride + seg_off + m % seg_len */
+    int64_t seg_stride, seg_off;
+    float* stat_part;         /* NULL or float2 partials of the stored values (see stat_mode) */
+    int32_t stat_mode;        /* 1: [M][P] per row;  2: [ceil(M/32)][P] per 32 rows;  P = vpt_gemm_stat_parts(N) */
+} vpt_gemm_args;
+
+int vpt_gemm_bf16(const vpt_gemm_args* args, void* stream);
+/* Number of statistics partials per row (or per 32 rows) the GEMM emits for an N-column output. */
+int vpt_gemm_stat_parts(int32_t N);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Stack-0 first convolution, fused:  u8 -> /255 -> Conv2d(3->C0, 3x3, pad 1) + bias -> ReLU -> max_pool2d(3, 2, 1)
+ * (lib/policy.py:39-45, lib/util.py:79-81 with bias, lib/impala_cnn.py:115-117).
+ *   img  u8   [F][H][W][3]      w  fp32 [C0][27] ordered (ky, kx, c), already divided by 255
+ *   out  bf16 [F][H/2][W/2][C0] stat_part float2 [F][(H/16)*(W/16)]   (H, W multiples of 16; C0 in {64,128,192,256})
+ * -------------------------------------------------------------------------------------------------------- */
+int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part,
+                       int32_t F, int32_t H, int32_t W, int32_t C0, void* stream);
+int vpt_firstconv_stat_parts(int32_t H, int32_t W);
+
+/* max_pool2d(kernel 3, stride 2, pad 1) on a non-negative NHWC bf16 tensor (lib/impala_cnn.py:117).
+ *   in [F][H][W][C] -> out [F][H/2][W/2][C];  stat_part float2 [F][vpt_pool_stat_parts()] */
+int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
+int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C);
+
+/* out[m][c] = (in[m][c] - mean_g) * rstd_g * gamma[c] + beta[c],  g = m / rows_per_group   (bf16 in, bf16 out)
+ * = nn.GroupNorm(1, C) on NHWC rows (lib/impala_cnn.py:119) and nn.LayerNorm(C) (lib/util.py:195, lib/policy.py:214).
+ * Optionally also writes an fp32 copy (out_f32, may be NULL) and emits statistics partials of the bf16 output:
+ * stat_part float2 [G][vpt_norm_stat_parts(rows_per_group, C)]. */
+int vpt_affine_norm(const void* in, const float* mr, const float* gamma, const float* beta, void* out, float* out_f32,
+                    float* stat_part, int64_t M, int32_t C, int32_t rows_per_group, void* stream);
+int vpt_norm_stat_parts(int32_t rows_per_group, int32_t C);
+
+/* mr[g] = (mean, rsqrt(var + eps)) from n_per_group float2 partials per group; count = elements per group. */
+int vpt_stats_finalize(const float* stat_part, float* mr, int64_t G, int32_t n_per_group, double count, float eps,
+                       void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Transformer-XL style KV memory + banded masked attention with learned relative-position bias
+ * (lib/masked_attention.py:11-94,161-178; lib/xf.py:18-71,265-271,334-391; lib/util.py:232-267).
+ * -------------------------------------------------------------------------------------------------------- */
+/* dst[b][dst_off + r][:] = src[b][src_off + r][:] for r < rows, converting fp32 <-> bf16 (KV memory load / store,
+ * lib/xf.py:378-381).  ld = row pitch in elements, *_bstride = batch pitch in elements. */
+int vpt_copy_rows(const void* src, int32_t src_f32, int64_t src_bstride, int64_t src_ld, int64_t src_off, void* dst,
+                  int32_t dst_f32, int64_t dst_bstride, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t rows,
+                  int32_t cols, void* stream);
+
+/* new_mask[b][j] = j < maxlen - min(t,maxlen) ? (mask[b][j + t] && !first[b]) : 1   (lib/masked_attention.py:86-92)
+ * mask_in may be NULL (= all zero, the state after initial_state()).  u8 0/1 arrays. */
+int vpt_state_mask_update(const uint8_t* mask_in, const uint8_t* first, int64_t first_stride, uint8_t* mask_out,
+                          int32_t B, int32_t t, int32_t maxlen, void* stream);
+
+/*   Q     bf16 [B][t][h]             (h = heads*128, head-major columns, lib/xf.py:96-103)
+ *   Kf,Vf bf16 [B][maxlen + t][h]    memory rows then the chunk's rows
+ *   R     fp32 [B][t][ld_r]          relative-attention queries, column head*nbasis + n (lib/xf.py:266-267)
+ *   b_nd  fp32 [nbasis][maxlen]
+ *   first u8 [B] (first[:,0] of the chunk), first_stride = elements between batch rows
+ *   smask u8 [B][maxlen] or NULL (all zero)
+ *   out   bf16 [B][t][h]
+ * logit = q.k / 128 + sum_n R[i][n] b_nd[n][d] over allowed keys, d = maxlen + i - j in [0, maxlen),
+ * allowed = j >= maxlen || (!first[b] && smask[b][j]).   causal = 0 selects the IDM variant (mask "none":
+ * every chunk key visible, no memory, no relative bias; lib/policy.py:342-392). */
+int vpt_attention(const void* Q, const void* Kf, const void* Vf, const float* R, int64_t ld_r, const float* b_nd,
+                  const uint8_t* first, int64_t first_stride, const uint8_t* smask, void* out, int32_t B, int32_t t,
+                  int32_t maxlen, int32_t heads, int32_t nbasis, int32_t causal, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Action heads (lib/action_head.py:163-207)
+ * -------------------------------------------------------------------------------------------------------- */
+/* out[r][0..n) = log_softmax(in[r][col0 .. col0+n))   in fp32 [rows][ld_in] (already divided by the temperature) */
+int vpt_log_softmax(const float* in, int64_t ld_in, int32_t col0, int32_t n, float* out, int64_t rows, void* stream);
+/* idx[r] = argmax_j(logits[r][j] - log(-log(u[r][j]))) with u==1 -> 0.999; u == NULL -> plain argmax (deterministic).
+ * Ties resolve to the lowest index (torch.argmax). */
+int vpt_gumbel_argmax(const float* logits, const float* u, int64_t* idx, int64_t rows, int32_t n, void* stream);
+/* lp[r] (+)= logits[r][idx[r]]   (lib/action_head.py:176-184) */
+int vpt_gather_logprob(const float* logits, const int64_t* idx, float* lp, int64_t rows, int32_t n, int32_t accumulate,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPT_B200_H_ */

@@ -1,0 +1,178 @@
+"""TEST-ONLY torch emulation of the C ABI ops (same signatures as video-pre-training_b200/ops.py).
+
+Purpose: check the HOST logic (weight re-layout, GroupNorm/LayerNorm folds, border-class tables, dense column
+permutation, KV-memory bookkeeping, launch order) against the oracle on CPU, where no GPU exists.  It mirrors what each
+kernel computes, including where values are rounded to bf16.  It is never importable from the product package."""
+import torch
+import torch.nn.functional as F
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def require_cuda(t):
+    pass
+
+
+def gemm_stat_parts(N):
+    nt = (N + 255) // 256
+    bn = (-(-N // nt) + 15) // 16 * 16
+    return -(-N // bn) * 2
+
+
+def _row_stats(v, rows_per_group):
+    """(mean, rstd) per group of rows from the stored values."""
+    G = v.shape[0] // rows_per_group
+    x = v.float().reshape(G, -1).double()
+    mean = x.mean(1)
+    var = (x * x).mean(1) - mean * mean
+    return torch.stack([mean, 1.0 / torch.sqrt(var.clamp(min=0) + 1e-5)], 1).float()
+
+
+def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, S2=None, relu=0, out_scale=1.0,
+         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0):
+    Af = A.float()
+    if conv is not None:
+        H, W, Cin = conv
+        x = Af.reshape(-1, H, W, Cin).permute(0, 3, 1, 2)
+        w = Bw.float().reshape(N, 3, 3, Cin).permute(0, 3, 1, 2)
+        acc = F.conv2d(x, w, padding=1).permute(0, 2, 3, 1).reshape(M, N)
+        pix = torch.arange(M) % (H * W)
+        y, xx = pix // W, pix % W
+        cy = torch.where(y == 0, 0, torch.where(y == H - 1, 2, 1))
+        cx = torch.where(xx == 0, 0, torch.where(xx == W - 1, 2, 1))
+        cls = cy * 3 + cx
+    else:
+        acc = Af.reshape(M, K) @ Bw.float().T
+        cls = torch.zeros(M, dtype=torch.long)
+    v = acc
+    s1 = S1.reshape(-1, N)[cls] if S1 is not None else 0.0
+    s2 = S2.reshape(-1, N)[cls] if S2 is not None else 0.0
+    if mr is not None:
+        g = torch.arange(M) // rows_per_group
+        a, b = mr[g, 1:2], (mr[g, 1] * mr[g, 0])[:, None]
+        v = a * acc - b * s1 + s2
+    else:
+        v = acc + s2
+    if relu == 1:
+        v = v.relu()
+    if residual is not None:
+        v = v + residual.reshape(M, N).float()
+    if relu == 2:
+        v = v.relu()
+    v = v * out_scale
+    v = v.to(out.dtype)
+    o2 = out.reshape(-1, out.shape[-1])
+    if seg is not None:
+        sl, ss, so = seg
+        m = torch.arange(M)
+        rows = (m // sl) * ss + so + m % sl
+        o2[rows, :N] = v
+    else:
+        o2[:M, :N] = v
+    if stat_part is not None:
+        vf = v.float()
+        P = gemm_stat_parts(N)
+        if stat_mode == 1:
+            pp = stat_part.reshape(-1, P, 2)
+            pp[:M] = 0
+            pp[:M, 0, 0] = vf.sum(1)
+            pp[:M, 0, 1] = (vf * vf).sum(1)
+        else:
+            r32 = (M + 31) // 32
+            pad = torch.zeros(r32 * 32, N)
+            pad[:M] = vf
+            pp = stat_part.reshape(-1, P, 2)
+            pp[:r32] = 0
+            pp[:r32, 0, 0] = pad.reshape(r32, -1).sum(1)
+            pp[:r32, 0, 1] = (pad * pad).reshape(r32, -1).sum(1)
+    return out
+
+
+def stats_finalize(part, G, n_per_group, count, eps=1e-5):
+    p = part.reshape(G, n_per_group, 2).double().sum(1)
+    mean = p[:, 0] / count
+    var = (p[:, 1] / count - mean * mean).clamp(min=0)
+    return torch.stack([mean, 1.0 / torch.sqrt(var + eps)], 1).float()
+
+
+def firstconv_pool(img, w, bias, C0):
+    F_, H, W, _ = img.shape
+    x = img.float().permute(0, 3, 1, 2)
+    wt = w.reshape(C0, 3, 3, 3).permute(0, 3, 1, 2)  # [C0][ky][kx][c] -> OIHW
+    y = F.relu(F.conv2d(x, wt, bias, padding=1))
+    y = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)
+    return y, _row_stats(y.reshape(F_, -1), 1)
+
+
+def maxpool3s2(x):
+    F_ = x.shape[0]
+    y = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)
+    return y, _row_stats(y.reshape(F_, -1), 1)
+
+
+def affine_norm(x, mr, gamma, beta, rows_per_group, want_stats=False, want_f32=False):
+    Cc = x.shape[-1]
+    xf = x.float().reshape(-1, Cc)
+    g = torch.arange(xf.shape[0]) // rows_per_group
+    o = ((xf - mr[g, 0:1]) * mr[g, 1:2]) * gamma[None] + beta[None]
+    ob = o.to(BF16).reshape(x.shape)
+    mr_out = _row_stats(ob.reshape(-1, Cc), rows_per_group) if want_stats else None
+    return ob, (o.reshape(x.shape) if want_f32 else None), mr_out
+
+
+def copy_rows(src, src_off, dst, dst_off, rows):
+    if rows:
+        dst[:, dst_off:dst_off + rows] = src[:, src_off:src_off + rows].to(dst.dtype)
+
+
+def state_mask_update(mask_in, first_u8, t, maxlen):
+    B = first_u8.shape[0]
+    if mask_in is None:
+        mask_in = torch.zeros((B, 1, maxlen), dtype=torch.uint8)
+    nf = (first_u8[:, 0] == 0)[:, None, None]
+    keep = maxlen - min(t, maxlen)
+    old = (mask_in.reshape(B, 1, maxlen)[:, :, t:t + keep] != 0) & nf
+    return torch.cat([old, torch.ones((B, 1, maxlen - keep), dtype=torch.bool)], -1)
+
+
+def attention(Q, Kf, Vf, R, b_nd, first_u8, smask, B, t, maxlen, heads, causal=True):
+    h = Q.shape[-1]
+    D = h // heads
+    T = maxlen + t
+    q = Q.float().reshape(B, t, heads, D).permute(0, 2, 1, 3)
+    k = Kf.float().reshape(B, T, heads, D).permute(0, 2, 1, 3)
+    v = Vf.float().reshape(B, T, heads, D).permute(0, 2, 1, 3)
+    logit = q @ k.transpose(-1, -2) / D
+    if causal:
+        i = torch.arange(t)[:, None]
+        j = torch.arange(T)[None, :]
+        d = maxlen + i - j
+        band = (d >= 0) & (d < maxlen)
+        memok = torch.zeros(B, maxlen, dtype=torch.bool) if smask is None else (smask.reshape(B, maxlen) != 0)
+        memok = memok & (first_u8[:, 0] == 0)[:, None]
+        colok = torch.cat([memok, torch.ones(B, t, dtype=torch.bool)], 1)  # [B, T]
+        allowed = band[None] & colok[:, None, :]
+        E = R.float().reshape(B, t, heads, -1).permute(0, 2, 1, 3) @ b_nd.float()  # [B, heads, t, maxlen]
+        dd = d.clamp(0, maxlen - 1)[None, None].expand(B, heads, t, T)
+        extra = torch.gather(E, 3, dd)
+        logit = torch.where(allowed[:, None], logit + extra, torch.tensor(-float("inf")))
+    w = torch.softmax(logit, -1)
+    o = (w.to(BF16).float() @ v).permute(0, 2, 1, 3).reshape(B * t, h)
+    return o.to(BF16).reshape(Q.shape)
+
+
+def log_softmax(raw, col0, n):
+    return F.log_softmax(raw[:, col0:col0 + n].float(), -1)
+
+
+def gumbel_argmax(logits, u=None):
+    if u is None:
+        return torch.argmax(logits, -1)
+    u = u.clone()
+    u[u == 1.0] = 0.999
+    return torch.argmax(logits - torch.log(-torch.log(u)), -1)
+
+
+def gather_logprob(logits, idx, lp=None):
+    r = logits.gather(-1, idx.long().unsqueeze(-1)).squeeze(-1)
+    return r if lp is None else lp + r

@@ -1,0 +1,296 @@
+// HBM-bound helper kernels of the CNN / transformer path: statistics finalisation, max-pool, affine normalisation
+// (GroupNorm(1) / LayerNorm application), KV-memory row copies, state-mask roll.  All are coalesced 16-byte-vector
+// streaming kernels; grids are sized from the data (>= several waves of 148 SMs at bench sizes).
+#pragma once
+#include "common.cuh"
+
+namespace vpt {
+
+// block-wide (sum, sumsq) reduction in a fixed order (deterministic); result valid in thread 0
+__device__ __forceinline__ float2 block_sum2(float s, float ss) {
+    __shared__ float red[2][32];
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (l == 0) {
+        red[0][w] = s;
+        red[1][w] = ss;
+    }
+    __syncthreads();
+    float2 r = make_float2(0.f, 0.f);
+    if (w == 0) {
+        float a = l < nw ? red[0][l] : 0.f, b = l < nw ? red[1][l] : 0.f;
+        a = warp_sum(a);
+        b = warp_sum(b);
+        r = make_float2(a, b);
+    }
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// mr[g] = (mean, rstd) from float2 partials
+// ---------------------------------------------------------------------------------------------------------
+__global__ void stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ mr, long long G, int n_per_group,
+                                      double inv_count, float eps) {
+    // one warp per group; lanes stride over the partials, doubles for the final combination
+    const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= G) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0.0, ss = 0.0;
+    const float2* p = part + g * n_per_group;
+    for (int i = lane; i < n_per_group; i += 32) {
+        float2 v = __ldg(p + i);
+        s += (double)v.x;
+        ss += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+        const double mean = s * inv_count;
+        double var = ss * inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// max_pool2d(3, 2, 1) on non-negative NHWC bf16; 8 channels (16 B) per thread; grid = (blocks_per_frame, F)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162 r = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                           float2* __restrict__ stat_part, int H, int W, int C8) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long f = blockIdx.y;
+    const int items = Ho * Wo * C8;
+    const uint4* fin = in + f * (long long)H * W * C8;
+    uint4* fout = out + f * (long long)items;
+    float s = 0.f, ss = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
+        const int c = i % C8, px = (i / C8) % Wo, py = i / (C8 * Wo);
+        uint4 m = make_uint4(0, 0, 0, 0);  // inputs are >= 0 (post-ReLU), so 0 == -inf padding
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = 2 * py + dy;
+            if (y < 0 || y >= H) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = 2 * px + dx;
+                if (x < 0 || x >= W) continue;
+                const uint4 v = __ldg(fin + ((long long)y * W + x) * C8 + c);
+                m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
+                m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
+            }
+        }
+        fout[i] = m;
+        const uint32_t w4[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
+            s += a + b;
+            ss = fmaf(a, a, fmaf(b, b, ss));
+        }
+    }
+    if (stat_part) {
+        const float2 r = block_sum2(s, ss);
+        if (threadIdx.x == 0) stat_part[f * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out = (in - mean_g) * rstd_g * gamma[c] + beta[c]; grid = (blocks_per_group, G)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) affine_norm_kernel(const uint4* __restrict__ in, const float2* __restrict__ mr,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            uint4* __restrict__ out, float* __restrict__ out_f32,
+                                                            float2* __restrict__ stat_part, long long items_per_group, int C8) {
+    const long long g = blockIdx.y;
+    const float2 st = __ldg(mr + g);
+    const float mean = st.x, rstd = st.y;
+    const uint4* gin = in + g * items_per_group;
+    uint4* gout = out + g * items_per_group;
+    float s = 0.f, ss = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items_per_group; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const uint4 v = __ldg(gin + i);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+        float x[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y), bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = fmaf((x[j] - mean) * rstd, ga[j], be[j]);
+        uint4 o;
+        o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]); o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+        gout[i] = o;
+        if (out_f32) {
+            float4* of = reinterpret_cast<float4*>(out_f32 + (g * items_per_group + i) * 8);
+            of[0] = make_float4(x[0], x[1], x[2], x[3]);
+            of[1] = make_float4(x[4], x[5], x[6], x[7]);
+        }
+        const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
+            s += a + b;
+            ss = fmaf(a, a, fmaf(b, b, ss));
+        }
+    }
+    if (stat_part) {
+        const float2 r = block_sum2(s, ss);
+        if (threadIdx.x == 0) stat_part[g * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// strided row copy with fp32 <-> bf16 conversion (KV memory load/store); 8 elements per thread
+// ---------------------------------------------------------------------------------------------------------
+template <bool SRC_F32, bool DST_F32>
+__global__ void __launch_bounds__(256) copy_rows_kernel(const void* __restrict__ src, long long src_bstride, long long src_ld,
+                                                          long long src_off, void* __restrict__ dst, long long dst_bstride,
+                                                          long long dst_ld, long long dst_off, int rows, int cols8) {
+    const int b = blockIdx.y;
+    const long long n = (long long)rows * cols8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols8), c = (int)(i % cols8) * 8;
+        const long long so = b * src_bstride + (src_off + r) * src_ld + c;
+        const long long dofs = b * dst_bstride + (dst_off + r) * dst_ld + c;
+        float x[8];
+        if (SRC_F32) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + so));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + so) + 1);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bb.x; x[5] = bb.y; x[6] = bb.z; x[7] = bb.w;
+        } else {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + so));
+            x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
+            x[4] = bf16_lo(v.z); x[5] = bf16_hi(v.z); x[6] = bf16_lo(v.w); x[7] = bf16_hi(v.w);
+        }
+        if (DST_F32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + dofs);
+            o[0] = make_float4(x[0], x[1], x[2], x[3]);
+            o[1] = make_float4(x[4], x[5], x[6], x[7]);
+        } else {
+            uint4 o;
+            o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]); o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + dofs) = o;
+        }
+    }
+}
+
+__global__ void state_mask_update_kernel(const uint8_t* __restrict__ mask_in, const uint8_t* __restrict__ first, long long first_stride,
+                                         uint8_t* __restrict__ mask_out, int B, int t, int maxlen) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * maxlen) return;
+    const int b = i / maxlen, j = i % maxlen;
+    const int keep = maxlen - min(t, maxlen);  // old entries that survive the roll
+    uint8_t v = 1;
+    if (j < keep) {
+        const uint8_t old = mask_in ? mask_in[(long long)b * maxlen + j + t] : 0;
+        v = (old != 0 && first[b * first_stride] == 0) ? 1 : 0;
+    }
+    mask_out[i] = v;
+}
+
+}  // namespace vpt
+
+extern "C" int vpt_stats_finalize(const float* stat_part, float* mr, int64_t G, int32_t n_per_group, double count, float eps,
+                                  void* stream) {
+    using namespace vpt;
+    VPT_CHECK(stat_part && mr && G > 0 && n_per_group > 0 && count > 0, "vpt_stats_finalize: bad arguments");
+    const int wpb = 8;
+    const long long blocks = (G + wpb - 1) / wpb;
+    stats_finalize_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(stat_part), reinterpret_cast<float2*>(mr), G, n_per_group, 1.0 / count, eps);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}
+
+static inline int vpt_blocks_for(long long items, int per_block, int cap) {
+    long long b = (items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+
+extern "C" int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C) {
+    return vpt_blocks_for((long long)(H / 2) * (W / 2) * (C / 8), 2048, 64);
+}
+
+extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(in && out && F > 0, "vpt_maxpool3s2: null argument");
+    VPT_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vpt_maxpool3s2: need even H, W and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
+    VPT_CHECK(F <= 65535, "vpt_maxpool3s2: at most 65535 frames per call (got %d)", F);
+    dim3 grid(vpt_pool_stat_parts(H, W, C), F);
+    maxpool3s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
+                                                            reinterpret_cast<float2*>(stat_part), H, W, C / 8);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}
+
+extern "C" int vpt_norm_stat_parts(int32_t rows_per_group, int32_t C) {
+    return vpt_blocks_for((long long)rows_per_group * (C / 8), 2048, 64);
+}
+
+extern "C" int vpt_affine_norm(const void* in, const float* mr, const float* gamma, const float* beta, void* out, float* out_f32,
+                               float* stat_part, int64_t M, int32_t C, int32_t rows_per_group, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(in && mr && gamma && beta && out, "vpt_affine_norm: null argument");
+    VPT_CHECK(C % 8 == 0 && rows_per_group > 0 && M % rows_per_group == 0, "vpt_affine_norm: need C %% 8 == 0 and M %% rows_per_group == 0");
+    const long long G = M / rows_per_group;
+    const long long items = (long long)rows_per_group * (C / 8);
+    const int bpg = vpt_norm_stat_parts(rows_per_group, C);
+    // grid.y is limited to 65535: loop over slabs of groups
+    for (long long g0 = 0; g0 < G; g0 += 65535) {
+        const long long gn = (G - g0 < 65535) ? (G - g0) : 65535;
+        dim3 grid(bpg, (unsigned)gn);
+        affine_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(in) + g0 * items, reinterpret_cast<const float2*>(mr) + g0, gamma, beta,
+            reinterpret_cast<uint4*>(out) + g0 * items, out_f32 ? out_f32 + g0 * items * 8 : nullptr,
+            stat_part ? reinterpret_cast<float2*>(stat_part) + g0 * bpg : nullptr, items, C / 8);
+        VPT_LAUNCH_CHECK();
+    }
+    return VPT_OK;
+}
+
+extern "C" int vpt_copy_rows(const void* src, int32_t src_f32, int64_t src_bstride, int64_t src_ld, int64_t src_off, void* dst,
+                             int32_t dst_f32, int64_t dst_bstride, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t rows,
+                             int32_t cols, void* stream) {
+    using namespace vpt;
+    if (rows == 0 || B == 0) return VPT_OK;
+    VPT_CHECK(src && dst && B > 0 && rows > 0 && cols > 0, "vpt_copy_rows: bad arguments");
+    VPT_CHECK(cols % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0 && src_bstride % 8 == 0 && dst_bstride % 8 == 0,
+              "vpt_copy_rows: cols / pitches must be multiples of 8");
+    VPT_CHECK(B <= 65535, "vpt_copy_rows: B too large");
+    dim3 grid(vpt_blocks_for((long long)rows * (cols / 8), 1024, 1024), B);
+    cudaStream_t s = (cudaStream_t)stream;
+#define VPT_CR(SF, DF)                                                                                                        \
+    copy_rows_kernel<SF, DF><<<grid, 256, 0, s>>>(src, src_bstride, src_ld, src_off, dst, dst_bstride, dst_ld, dst_off, rows, \
+                                                  cols / 8)
+    if (src_f32 && dst_f32) VPT_CR(true, true);
+    else if (src_f32) VPT_CR(true, false);
+    else if (dst_f32) VPT_CR(false, true);
+    else VPT_CR(false, false);
+#undef VPT_CR
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}
+
+extern "C" int vpt_state_mask_update(const uint8_t* mask_in, const uint8_t* first, int64_t first_stride, uint8_t* mask_out,
+                                     int32_t B, int32_t t, int32_t maxlen, void* stream) {
+    using namespace vpt;
+    if (maxlen == 0 || B == 0) return VPT_OK;
+    VPT_CHECK(first && mask_out && B > 0 && t > 0 && maxlen > 0, "vpt_state_mask_update: bad arguments");
+    const int n = B * maxlen;
+    state_mask_update_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mask_in, first, first_stride, mask_out, B, t, maxlen);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}

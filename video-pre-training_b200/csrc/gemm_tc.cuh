@@ -1,0 +1,497 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   warp 0 (one lane)  : TMA producer  -- A tile (128 rows x 64 bf16, 128B-swizzled) + B tile (block_n x 64)
+//   warp 1 (one lane)  : tcgen05.mma issuer, accumulators in TMEM (2 stages x 256 columns)
+//   warps 2..9         : epilogue -- tcgen05.ld -> norm-fold / bias / ReLU / residual -> bf16|fp32 store + statistics
+//
+// Convolution: the K loop runs over (tap, 64-channel block); the A tile of tap (dy,dx) is ONE 4-D TMA box of the raw
+// NHWC activation tensor at pixel offset (dy,dx) -- TMA zero-fills out-of-image elements, which is exactly pad=1 --
+// landing in shared memory as 128 pixel rows of 128 B, i.e. the canonical K-major SWIZZLE_128B UMMA operand.
+// GroupNorm/LayerNorm on the input is folded into the epilogue (see include/vpt_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace vpt {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kNumEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;
+constexpr int kMaxStages = 8;
+constexpr int kAccStageCols = 256;
+constexpr uint32_t kStageBytesA = kBlockM * kBlockK * 2;
+
+struct GemmParams {
+    int M, N, K;
+    int block_n, num_m_tiles, num_n_tiles, k_iters, num_stages;
+    int conv, H, W, cin_blocks, px_per_frame;
+    // epilogue
+    const float* mr;
+    int rows_per_group;
+    const float* S1;
+    const float* S2;
+    int relu;
+    float out_scale;
+    const void* residual;
+    int residual_f32;
+    long long ld_res;
+    void* out;
+    int out_f32;
+    long long ld_out;
+    int seg_len;
+    long long seg_stride, seg_off;
+    float* stat_part;
+    int stat_mode;
+};
+
+__device__ __forceinline__ void advance(int& stage, uint32_t& phase, int num_stages) {
+    if (++stage == num_stages) {
+        stage = 0;
+        phase ^= 1u;
+    }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // carve: [A stages][B stages][barriers]; operand tiles need 1024-byte alignment for SWIZZLE_128B
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const uint32_t stage_bytes_b = (uint32_t)p.block_n * kBlockK * 2;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.num_stages * kStageBytesA;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.num_stages * stage_bytes_b);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kMaxStages;
+    uint64_t* tmem_full_bar = bars + 2 * kMaxStages;
+    uint64_t* tmem_empty_bar = bars + 2 * kMaxStages + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < p.num_stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+                const int m0 = m_tile * kBlockM, n0 = n_tile * p.block_n;
+                int f0 = 0, y0 = 0;
+                if (p.conv) {
+                    f0 = m0 / p.px_per_frame;
+                    y0 = (m0 % p.px_per_frame) / p.W;
+                }
+                for (int it = 0; it < p.k_iters; ++it) {
+                    if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1u, 0x100u))) break;
+                    mbar_expect_tx(&full_bar[stage], kStageBytesA + stage_bytes_b);
+                    uint8_t* sa = smem_a + (size_t)stage * kStageBytesA;
+                    uint8_t* sb = smem_b + (size_t)stage * stage_bytes_b;
+                    if (p.conv) {
+                        const int tap = it / p.cin_blocks, cb = it - tap * p.cin_blocks;
+                        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBlockK, dx, y0 + dy, f0);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], it * kBlockK, m0);
+                    }
+                    tma_load_2d(sb, &tmB, &full_bar[stage], it * kBlockK, n0);
+                    advance(stage, phase, p.num_stages);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+                if (!(ok = mbar_wait(&tmem_empty_bar[as], aphase ^ 1u, 0x200u))) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStageCols);
+                for (int it = 0; it < p.k_iters; ++it) {
+                    if (!(ok = mbar_wait(&full_bar[stage], phase, 0x300u))) break;
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kStageBytesA);
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * stage_bytes_b);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                  (uint32_t)((it | k) != 0));
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    advance(stage, phase, p.num_stages);
+                }
+                if (ok) umma_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int chalf = ew >> 2;                    // column half
+        const int nchunks = (p.block_n + 31) >> 5;
+        const int c_begin = chalf == 0 ? 0 : (nchunks + 1) >> 1;
+        const int c_end = chalf == 0 ? (nchunks + 1) >> 1 : nchunks;
+        const int P = p.num_n_tiles * 2;
+        const bool tab_vec = (p.conv == 0) || ((p.N & 3) == 0);
+        const bool out_vec = ((p.ld_out & 7) == 0);
+        const bool res_vec = ((p.ld_res & 7) == 0);
+        int local = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
+            const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+            const int m0 = m_tile * kBlockM, n0 = n_tile * p.block_n;
+            const int as = local & 1;
+            const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
+            const int m = m0 + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            // per-row constants
+            float ga = 1.f, gb = 0.f;
+            if (p.mr != nullptr && row_ok) {
+                const int g = m / p.rows_per_group;
+                const float mean = __ldg(p.mr + 2 * g), rstd = __ldg(p.mr + 2 * g + 1);
+                ga = rstd;
+                gb = rstd * mean;
+            }
+            int cls = 0;
+            if (p.conv) {
+                const int pix = m % p.px_per_frame;
+                const int y = pix / p.W, x = pix - y * p.W;
+                const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+                const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+                cls = cy * 3 + cx;
+            }
+            const float* s1row = p.S1 ? p.S1 + (size_t)cls * p.N : nullptr;
+            const float* s2row = p.S2 ? p.S2 + (size_t)cls * p.N : nullptr;
+            long long orow = m;
+            if (p.seg_len > 0) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
+            float st_s = 0.f, st_ss = 0.f;
+
+            if (!(ok = mbar_wait(&tmem_full_bar[as], aphase, 0x400u))) break;
+            tc_fence_after();
+            for (int c = c_begin; c < c_end; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + c * 32), acc);
+                tmem_ld_wait();
+                const int nb = n0 + c * 32;
+                const int lim = min(32, min(p.block_n - c * 32, p.N - nb));  // valid columns in this chunk
+                if (!row_ok || lim <= 0) continue;
+                float v[32];
+                const bool full = (lim == 32);
+                // ---- fold: v = ga*acc - gb*S1 + S2
+                if (full && tab_vec) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 a1 = s1row ? __ldg(reinterpret_cast<const float4*>(s1row + nb) + q) : make_float4(0, 0, 0, 0);
+                        float4 a2 = s2row ? __ldg(reinterpret_cast<const float4*>(s2row + nb) + q) : make_float4(0, 0, 0, 0);
+                        v[4 * q + 0] = fmaf(ga, __uint_as_float(acc[4 * q + 0]), fmaf(-gb, a1.x, a2.x));
+                        v[4 * q + 1] = fmaf(ga, __uint_as_float(acc[4 * q + 1]), fmaf(-gb, a1.y, a2.y));
+                        v[4 * q + 2] = fmaf(ga, __uint_as_float(acc[4 * q + 2]), fmaf(-gb, a1.z, a2.z));
+                        v[4 * q + 3] = fmaf(ga, __uint_as_float(acc[4 * q + 3]), fmaf(-gb, a1.w, a2.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float a1 = 0.f, a2 = 0.f;
+                        if (j < lim) {
+                            if (s1row) a1 = __ldg(s1row + nb + j);
+                            if (s2row) a2 = __ldg(s2row + nb + j);
+                        }
+                        v[j] = fmaf(ga, __uint_as_float(acc[j]), fmaf(-gb, a1, a2));
+                    }
+                }
+                if (p.relu == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                // ---- residual
+                if (p.residual != nullptr) {
+                    if (p.residual_f32) {
+                        const float* rp = reinterpret_cast<const float*>(p.residual) + (size_t)m * p.ld_res + nb;
+                        if (full && (p.ld_res & 3) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 r = __ldg(reinterpret_cast<const float4*>(rp) + q);
+                                v[4 * q + 0] += r.x; v[4 * q + 1] += r.y; v[4 * q + 2] += r.z; v[4 * q + 3] += r.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < lim) v[j] += __ldg(rp + j);
+                        }
+                    } else {
+                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)m * p.ld_res + nb;
+                        if (full && res_vec) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 r = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+                                v[8 * q + 0] += bf16_lo(r.x); v[8 * q + 1] += bf16_hi(r.x);
+                                v[8 * q + 2] += bf16_lo(r.y); v[8 * q + 3] += bf16_hi(r.y);
+                                v[8 * q + 4] += bf16_lo(r.z); v[8 * q + 5] += bf16_hi(r.z);
+                                v[8 * q + 6] += bf16_lo(r.w); v[8 * q + 7] += bf16_hi(r.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < lim) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                }
+                if (p.relu == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (p.out_scale != 1.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+                }
+                // ---- store (+ statistics of the stored values)
+                if (p.out_f32) {
+                    float* op = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ld_out + nb;
+                    if (full && (p.ld_out & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            reinterpret_cast<float4*>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < lim) op[j] = v[j];
+                    }
+                    if (p.stat_part) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < lim) {
+                                st_s += v[j];
+                                st_ss = fmaf(v[j], v[j], st_ss);
+                            }
+                    }
+                } else {
+                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ld_out + nb;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                    if (p.stat_part) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+                            if (2 * j < lim) { st_s += lo; st_ss = fmaf(lo, lo, st_ss); }
+                            if (2 * j + 1 < lim) { st_s += hi; st_ss = fmaf(hi, hi, st_ss); }
+                        }
+                    }
+                    if (full && out_vec) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            reinterpret_cast<uint4*>(op)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < lim) op[j] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+            }
+            // release the accumulator stage to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            // statistics partials
+            if (p.stat_part) {
+                if (p.stat_mode == 1) {
+                    if (row_ok)
+                        reinterpret_cast<float2*>(p.stat_part)[(size_t)m * P + n_tile * 2 + chalf] = make_float2(st_s, st_ss);
+                } else {
+                    const float s = warp_sum(st_s), ss = warp_sum(st_ss);
+                    const int g32 = (m0 + quarter * 32) >> 5;
+                    if (lane == 0 && (m0 + quarter * 32) < p.M)
+                        reinterpret_cast<float2*>(p.stat_part)[(size_t)g32 * P + n_tile * 2 + chalf] = make_float2(s, ss);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    return fn;
+}
+
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                          const cuuint32_t* box) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return VPT_ERR_CUDA;
+    }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+        return VPT_ERR_CUDA;
+    }
+    return VPT_OK;
+}
+
+static inline void choose_block_n(int N, int* block_n, int* n_tiles) {
+    int nt = (N + 255) / 256;
+    int bn = (N + nt - 1) / nt;
+    bn = (bn + 15) / 16 * 16;
+    if (bn < 16) bn = 16;
+    *block_n = bn;
+    *n_tiles = (N + bn - 1) / bn;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_num_sms;
+}
+
+}  // namespace vpt
+
+extern "C" int vpt_gemm_stat_parts(int32_t N) {
+    int bn, nt;
+    vpt::choose_block_n(N, &bn, &nt);
+    return nt * 2;
+}
+
+extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(a != nullptr && a->A && a->B && a->out, "vpt_gemm_bf16: null operand");
+    VPT_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "vpt_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+    VPT_CHECK(a->K % 8 == 0, "vpt_gemm_bf16: K=%d must be a multiple of 8 (16-byte rows for TMA)", a->K);
+    VPT_CHECK(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0, "vpt_gemm_bf16: A/B must be 16-byte aligned");
+    VPT_CHECK(a->mr == nullptr || a->rows_per_group > 0, "vpt_gemm_bf16: rows_per_group must be > 0 with mr");
+    VPT_CHECK(a->stat_part == nullptr || a->stat_mode == 1 || a->stat_mode == 2, "vpt_gemm_bf16: bad stat_mode %d", a->stat_mode);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    choose_block_n(a->N, &p.block_n, &p.num_n_tiles);
+    p.num_m_tiles = (a->M + kBlockM - 1) / kBlockM;
+    p.conv = a->conv;
+    CUtensorMap tmA, tmB;
+    if (a->conv) {
+        const int H = a->H, W = a->W, C = a->Cin;
+        VPT_CHECK(H >= 2 && W >= 2 && C > 0 && C % 64 == 0, "vpt_gemm_bf16(conv): need H,W >= 2 and Cin %% 64 == 0 (H=%d W=%d Cin=%d)", H, W, C);
+        VPT_CHECK(a->K == 9 * C, "vpt_gemm_bf16(conv): K=%d != 9*Cin=%d", a->K, 9 * C);
+        const int pxpf = H * W;
+        VPT_CHECK(a->M % pxpf == 0, "vpt_gemm_bf16(conv): M=%d not a multiple of H*W=%d", a->M, pxpf);
+        VPT_CHECK(128 % W == 0 && W <= 128, "vpt_gemm_bf16(conv): W=%d must divide 128", W);
+        int tile_rows, tile_frames;
+        if (pxpf >= 128) {
+            VPT_CHECK(pxpf % 128 == 0, "vpt_gemm_bf16(conv): H*W=%d must be a multiple of 128", pxpf);
+            tile_rows = 128 / W; tile_frames = 1;
+        } else {
+            VPT_CHECK(128 % pxpf == 0, "vpt_gemm_bf16(conv): H*W=%d must divide 128", pxpf);
+            tile_rows = H; tile_frames = 128 / pxpf;
+        }
+        const cuuint64_t F = (cuuint64_t)(a->M / pxpf);
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, F};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)tile_rows, (cuuint32_t)tile_frames};
+        int r = make_tmap_bf16(&tmA, a->A, 4, dims, strides, box);
+        if (r) return r;
+        p.H = H; p.W = W; p.cin_blocks = C / 64; p.px_per_frame = pxpf;
+        p.k_iters = 9 * p.cin_blocks;
+    } else {
+        cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->M};
+        cuuint64_t strides[1] = {(cuuint64_t)a->K * 2};
+        cuuint32_t box[2] = {64, 128};
+        int r = make_tmap_bf16(&tmA, a->A, 2, dims, strides, box);
+        if (r) return r;
+        p.k_iters = (a->K + kBlockK - 1) / kBlockK;
+        p.px_per_frame = 1; p.W = 1; p.H = 1;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
+        cuuint64_t strides[1] = {(cuuint64_t)a->K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.block_n};
+        int r = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
+        if (r) return r;
+    }
+    const uint32_t stage_bytes = kStageBytesA + (uint32_t)p.block_n * kBlockK * 2;
+    int stages = (int)(200 * 1024 / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    p.num_stages = stages;
+    const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 16;
+    p.mr = a->mr; p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+    p.S1 = a->mr ? a->S1 : nullptr;
+    p.S2 = a->S2;
+    p.relu = a->relu; p.out_scale = a->out_scale;
+    p.residual = a->residual; p.residual_f32 = a->residual_f32; p.ld_res = a->ld_res;
+    p.out = a->out; p.out_f32 = a->out_f32; p.ld_out = a->ld_out;
+    p.seg_len = a->seg_len; p.seg_stride = a->seg_stride; p.seg_off = a->seg_off;
+    p.stat_part = a->stat_part; p.stat_mode = a->stat_mode;
+    VPT_CHECK(!(a->mr && !a->S1), "vpt_gemm_bf16: mr given without S1");
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        VPT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    int grid = num_sms();
+    if (grid <= 0) grid = 148;
+    if (grid > tiles) grid = tiles;
+    gemm_tc_kernel<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}

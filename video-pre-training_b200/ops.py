@@ -1,0 +1,161 @@
+"""Tensor-level wrappers of the C ABI: torch tensors in, torch tensors out, everything enqueued on torch's current
+CUDA stream.  torch is used for device memory and streams only -- all arithmetic happens in libvpt_b200.so."""
+import ctypes as C
+
+import torch
+
+from . import _native as nat
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t):
+    if not t.is_cuda:
+        raise nat.NativeError("vpt_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise nat.NativeError("vpt_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, S2=None, relu=0, out_scale=1.0,
+         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0):
+    """out = epilogue(A @ Bw^T); see struct vpt_gemm_args."""
+    _cuda(A, Bw, out)
+    a = nat.GemmArgs()
+    a.A, a.B, a.M, a.N, a.K = _p(A), _p(Bw), M, N, K
+    if conv is not None:
+        a.conv, (a.H, a.W, a.Cin) = 1, conv
+    a.mr, a.rows_per_group, a.S1, a.S2 = _p(mr), rows_per_group, _p(S1), _p(S2)
+    a.relu, a.out_scale = relu, out_scale
+    if residual is not None:
+        a.residual, a.residual_f32, a.ld_res = _p(residual), int(residual.dtype == F32), residual.stride(-2)
+    a.out, a.out_f32 = _p(out), int(out.dtype == F32)
+    a.ld_out = ld_out if ld_out is not None else out.stride(-2)
+    if seg is not None:
+        a.seg_len, a.seg_stride, a.seg_off = seg
+    a.stat_part, a.stat_mode = _p(stat_part), stat_mode
+    nat.check(nat.lib().vpt_gemm_bf16(C.byref(a), _stream()), "vpt_gemm_bf16")
+    return out
+
+
+def gemm_stat_parts(N):
+    return nat.lib().vpt_gemm_stat_parts(N)
+
+
+def stats_finalize(part, G, n_per_group, count, eps=1e-5):
+    mr = torch.empty((G, 2), dtype=F32, device=part.device)
+    nat.check(nat.lib().vpt_stats_finalize(_p(part), _p(mr), G, n_per_group, float(count), eps, _stream()), "vpt_stats_finalize")
+    return mr
+
+
+def firstconv_pool(img, w, bias, C0):
+    """img u8 [F,H,W,3] -> (bf16 [F,H/2,W/2,C0], per-frame (mean, rstd))."""
+    _cuda(img, w, bias)
+    F_, H, W, _ = img.shape
+    out = torch.empty((F_, H // 2, W // 2, C0), dtype=BF16, device=img.device)
+    P = nat.lib().vpt_firstconv_stat_parts(H, W)
+    part = torch.empty((F_, P, 2), dtype=F32, device=img.device)
+    nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, _stream()), "vpt_firstconv_pool")
+    return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * C0)
+
+
+def maxpool3s2(x):
+    """bf16 [F,H,W,C] (>= 0) -> (bf16 [F,H/2,W/2,C], per-frame (mean, rstd))."""
+    _cuda(x)
+    F_, H, W, Cc = x.shape
+    out = torch.empty((F_, H // 2, W // 2, Cc), dtype=BF16, device=x.device)
+    P = nat.lib().vpt_pool_stat_parts(H, W, Cc)
+    part = torch.empty((F_, P, 2), dtype=F32, device=x.device)
+    nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), F_, H, W, Cc, _stream()), "vpt_maxpool3s2")
+    return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * Cc)
+
+
+def affine_norm(x, mr, gamma, beta, rows_per_group, want_stats=False, want_f32=False):
+    """(x - mean_g) * rstd_g * gamma + beta on [M, C] rows; returns (bf16 out, fp32 out | None, (mean, rstd) of out | None)."""
+    _cuda(x, mr, gamma, beta)
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    out = torch.empty_like(x)
+    out32 = torch.empty(x.shape, dtype=F32, device=x.device) if want_f32 else None
+    part, P = None, 0
+    G = M // rows_per_group
+    if want_stats:
+        P = nat.lib().vpt_norm_stat_parts(rows_per_group, Cc)
+        part = torch.empty((G, P, 2), dtype=F32, device=x.device)
+    nat.check(nat.lib().vpt_affine_norm(_p(x), _p(mr), _p(gamma), _p(beta), _p(out), _p(out32), _p(part), M, Cc, rows_per_group,
+                                        _stream()), "vpt_affine_norm")
+    mr_out = stats_finalize(part, G, P, rows_per_group * Cc) if want_stats else None
+    return out, out32, mr_out
+
+
+def copy_rows(src, src_off, dst, dst_off, rows):
+    """dst[:, dst_off:dst_off+rows, :] = src[:, src_off:src_off+rows, :] for [B, L, C] tensors (fp32 <-> bf16)."""
+    _cuda(src, dst)
+    if rows == 0:
+        return
+    B, _, Cc = src.shape
+    nat.check(nat.lib().vpt_copy_rows(_p(src), int(src.dtype == F32), src.stride(0), src.stride(1), src_off, _p(dst),
+                                      int(dst.dtype == F32), dst.stride(0), dst.stride(1), dst_off, B, rows, Cc, _stream()),
+              "vpt_copy_rows")
+
+
+def state_mask_update(mask_in, first_u8, t, maxlen):
+    """mask_in: bool (B,1,maxlen) or None; first_u8: u8 view of first (B,T); returns new bool (B,1,maxlen)."""
+    B = first_u8.shape[0]
+    out = torch.empty((B, 1, maxlen), dtype=torch.bool, device=first_u8.device)
+    if maxlen > 0:
+        nat.check(nat.lib().vpt_state_mask_update(_p(mask_in), _p(first_u8), first_u8.stride(0), _p(out), B, t, maxlen, _stream()),
+                  "vpt_state_mask_update")
+    return out
+
+
+def attention(Q, Kf, Vf, R, b_nd, first_u8, smask, B, t, maxlen, heads, causal=True):
+    _cuda(Q, Kf, Vf)
+    out = torch.empty_like(Q)
+    nbasis = b_nd.shape[0] if (causal and b_nd is not None) else 0
+    nat.check(nat.lib().vpt_attention(_p(Q), _p(Kf), _p(Vf), _p(R), R.stride(-2) if R is not None else 0, _p(b_nd),
+                                      _p(first_u8), first_u8.stride(0) if first_u8 is not None else 0, _p(smask), _p(out), B, t,
+                                      maxlen, heads, nbasis, int(causal), _stream()), "vpt_attention")
+    return out
+
+
+def log_softmax(raw, col0, n):
+    """raw fp32 [rows, ld] -> fp32 [rows, n] = log_softmax(raw[:, col0:col0+n])."""
+    rows = raw.shape[0]
+    out = torch.empty((rows, n), dtype=F32, device=raw.device)
+    nat.check(nat.lib().vpt_log_softmax(_p(raw), raw.stride(0), col0, n, _p(out), rows, _stream()), "vpt_log_softmax")
+    return out
+
+
+def gumbel_argmax(logits, u=None):
+    """logits fp32 [..., n] contiguous, u same shape or None -> int64 [...]."""
+    _cuda(logits)
+    logits = logits.contiguous()
+    n = logits.shape[-1]
+    rows = logits.numel() // n
+    idx = torch.empty(logits.shape[:-1], dtype=torch.int64, device=logits.device)
+    nat.check(nat.lib().vpt_gumbel_argmax(_p(logits), _p(u), _p(idx), rows, n, _stream()), "vpt_gumbel_argmax")
+    return idx
+
+
+def gather_logprob(logits, idx, lp=None):
+    logits = logits.contiguous()
+    idx = idx.contiguous()
+    n = logits.shape[-1]
+    rows = logits.numel() // n
+    acc = lp is not None
+    if lp is None:
+        lp = torch.empty(logits.shape[:-1], dtype=F32, device=logits.device)
+    nat.check(nat.lib().vpt_gather_logprob(_p(logits), _p(idx), _p(lp), rows, n, int(acc), _stream()), "vpt_gather_logprob")
+    return lp

@@ -1,0 +1,608 @@
+"""Drop-in replacements for the reference's policy classes (lib/policy.py) whose forward pass runs entirely in the
+hand-written sm_100a kernels of libvpt_b200.so.
+
+    MinecraftPolicy        lib/policy.py:83-224    forward(ob, state_in, context) / initial_state / output_latent_size
+    MinecraftAgentPolicy   lib/policy.py:227-339   forward / act / get_output_for_observation / get_logprob_of_action /
+                                                   get_kl_of_action_dists / v / initial_state
+    InverseActionPolicy    lib/policy.py:406-467   (see idm.py)
+
+Same constructor kwargs, same state pytree (list over layers of (state_mask bool (B,1,maxlen) | None, (K, V) fp32
+(B,maxlen,hidsize))), same `state_dict()` keys / shapes, so reference weight files load with
+`load_state_dict`.  Parameters are kept in fp32 exactly as the reference stores them; at first use (and whenever a
+parameter changes) they are re-laid-out for the kernels (`_Prepared`): conv weights OIHW -> [Cout][tap][Cin] bf16 with
+the input GroupNorm gamma folded in plus the 9 border-class fold tables, linear weights with LayerNorm folded, the
+`dense` columns permuted from C,H,W to H,W,C order.
+
+Inference only (the kernels have no backward yet): forward runs under no_grad and returns detached tensors.
+There is no CPU path: CPU tensors raise.
+"""
+import math
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .types import DictType
+
+BF16, F32 = torch.bfloat16, torch.float32
+NBASIS = 10  # lib/xf.py:259
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter schema + init (names / shapes / init scales of the reference)
+# ---------------------------------------------------------------------------------------------------------------
+class _Node(nn.Module):
+    """Bare container so that `state_dict()` keys nest exactly like the reference's module tree."""
+
+
+def _set(root: nn.Module, name: str, tensor: torch.Tensor, requires_grad=True):
+    parts = name.split(".")
+    m = root
+    for p in parts[:-1]:
+        if p not in m._modules:
+            m.add_module(p, _Node())
+        m = m._modules[p]
+    m.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=requires_grad))
+
+
+def _fanin(shape, scale):
+    """lib/util.py:67-73 / lib/torch_util.py:79: default torch init, then every output row L2-normalised to `scale`."""
+    w = torch.empty(shape)
+    nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    flat = w.reshape(shape[0], -1)
+    flat *= scale / flat.norm(dim=1, p=2, keepdim=True)
+    return w
+
+
+def _default_linear(out_f, in_f):
+    """nn.Linear default init (lib/action_head.py:150, lib/scaled_mse_head.py:24)."""
+    w = torch.empty(out_f, in_f)
+    nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    bound = 1 / math.sqrt(in_f)
+    return w, torch.empty(out_f).uniform_(-bound, bound)
+
+
+class NetConfig:
+    """The kwargs of lib/policy.py:96-126 that the transformer models use (agent.py:16-36)."""
+
+    def __init__(self, recurrence_type="transformer", impala_width=1, impala_chans=(16, 32, 32), obs_processing_width=256,
+                 hidsize=512, single_output=False, img_shape=None, scale_input_img=True, only_img_input=False,
+                 init_norm_kwargs=None, impala_kwargs=None, input_shape=None, active_reward_monitors=None, img_statistics=None,
+                 first_conv_norm=False, diff_mlp_embedding=False, attention_mask_style="clipped_causal", attention_heads=8,
+                 attention_memory_size=2048, use_pointwise_layer=True, pointwise_ratio=4, pointwise_use_activation=False,
+                 n_recurrence_layers=1, recurrence_is_residual=True, timesteps=None, use_pre_lstm_ln=True, **unused_kwargs):
+        init_norm_kwargs = init_norm_kwargs or {}
+        impala_kwargs = impala_kwargs or {}
+        # Only the configuration family of the released models is implemented in CUDA; anything else is refused loudly.
+        if recurrence_type != "transformer":
+            raise NotImplementedError("vpt_b200: only recurrence_type='transformer' (all released VPT models, agent.py:32)")
+        if init_norm_kwargs.get("group_norm_groups", None) != 1 or init_norm_kwargs.get("batch_norm", False):
+            raise NotImplementedError("vpt_b200: init_norm_kwargs must be {'batch_norm': False, 'group_norm_groups': 1} (agent.py:26)")
+        if impala_kwargs.get("post_pool_groups", None) != 1:
+            raise NotImplementedError("vpt_b200: impala_kwargs must be {'post_pool_groups': 1} (agent.py:24)")
+        if img_statistics is not None or not scale_input_img or diff_mlp_embedding or use_pre_lstm_ln:
+            raise NotImplementedError("vpt_b200: img_statistics / scale_input_img=False / diff_mlp_embedding / use_pre_lstm_ln unsupported")
+        if not (use_pointwise_layer and recurrence_is_residual) or pointwise_use_activation:
+            raise NotImplementedError("vpt_b200: needs use_pointwise_layer, recurrence_is_residual, no pointwise activation")
+        if attention_mask_style not in ("clipped_causal", "none"):
+            raise AssertionError("mask must be 'none' or 'clipped_causal'")  # lib/masked_attention.py:134
+        assert attention_memory_size >= 0  # lib/masked_attention.py:135
+        self.chans = tuple(int(impala_width * c) for c in impala_chans)
+        self.hidsize = hidsize
+        self.heads = attention_heads
+        self.timesteps = timesteps
+        self.maxlen = attention_memory_size - timesteps
+        self.mask_style = attention_mask_style
+        self.n_layers = n_recurrence_layers
+        self.img_shape = tuple(img_shape)
+        self.pointwise_ratio = pointwise_ratio
+        self.single_output = single_output
+        self.first_conv_norm = first_conv_norm
+        self.cnn_outsize = 256
+        assert hidsize % attention_heads == 0, "Embsize must be divisible by number of heads"  # lib/xf.py:98
+        if hidsize // attention_heads != 128:
+            raise NotImplementedError("vpt_b200: head_dim must be 128 (true of every VPT width)")
+        assert self.maxlen > 0 or self.mask_style == "none"  # lib/xf.py:256
+        H, W, Cin = self.img_shape
+        if Cin != 3 or H % 16 or W % 16 or any(c % 64 for c in self.chans):
+            raise NotImplementedError("vpt_b200: img must be (H,W,3) with H,W %% 16 == 0 and CNN channels %% 64 == 0")
+        self.final_hw = (H // 8, W // 8)
+
+
+def _net_schema(cfg: NetConfig) -> "OrderedDict[str, torch.Tensor]":
+    """Freshly initialised parameters in the reference's registration order (lib/impala_cnn.py, lib/util.py, lib/xf.py)."""
+    sd = OrderedDict()
+    p = "img_process.cnn"
+    cin = cfg.img_shape[2]
+    nstack = len(cfg.chans)
+    for i, c in enumerate(cfg.chans):
+        s = f"{p}.stacks.{i}"
+        has_norm = cfg.first_conv_norm if i == 0 else True
+        if has_norm:
+            sd[f"{s}.firstconv.norm.weight"], sd[f"{s}.firstconv.norm.bias"] = torch.ones(cin), torch.zeros(cin)
+        sd[f"{s}.firstconv.layer.weight"] = _fanin((c, cin, 3, 3), 1.0)
+        if not has_norm:
+            sd[f"{s}.firstconv.layer.bias"] = torch.zeros(c)
+        sd[f"{s}.n.weight"], sd[f"{s}.n.bias"] = torch.ones(c), torch.zeros(c)
+        bs = math.sqrt(math.sqrt(nstack) / math.sqrt(2))  # impala_cnn.py:164,105,30
+        for j in range(2):
+            for k in range(2):
+                q = f"{s}.blocks.{j}.conv{k}"
+                sd[f"{q}.norm.weight"], sd[f"{q}.norm.bias"] = torch.ones(c), torch.zeros(c)
+                sd[f"{q}.layer.weight"] = _fanin((c, c, 3, 3), bs)
+        cin = c
+    kd = cin * cfg.final_hw[0] * cfg.final_hw[1]
+    sd[f"{p}.dense.norm.weight"], sd[f"{p}.dense.norm.bias"] = torch.ones(kd), torch.zeros(kd)
+    sd[f"{p}.dense.layer.weight"] = _fanin((cfg.cnn_outsize, kd), 1.4)
+    sd["img_process.linear.norm.weight"], sd["img_process.linear.norm.bias"] = torch.ones(256), torch.zeros(256)
+    sd["img_process.linear.layer.weight"] = _fanin((cfg.hidsize, 256), 1.0)
+    h = cfg.hidsize
+    s_blk = cfg.n_layers ** -0.5 * 2 ** -0.5  # lib/util.py:101,154-155
+    s_att = math.sqrt(s_blk)                  # lib/xf.py:246
+    for l in range(cfg.n_layers):
+        b = f"recurrent_layer.blocks.{l}"
+        sd[f"{b}.mlp0.norm.weight"], sd[f"{b}.mlp0.norm.bias"] = torch.ones(h), torch.zeros(h)
+        sd[f"{b}.mlp0.layer.weight"] = _fanin((h * cfg.pointwise_ratio, h), 1.0)
+        sd[f"{b}.mlp1.layer.weight"] = _fanin((h, h * cfg.pointwise_ratio), s_blk)
+        sd[f"{b}.mlp1.layer.bias"] = torch.zeros(h)
+        sd[f"{b}.pre_r_ln.weight"], sd[f"{b}.pre_r_ln.bias"] = torch.ones(h), torch.zeros(h)
+        o = f"{b}.r.orc_block"
+        sd[f"{o}.b_nd"] = torch.randn(NBASIS, cfg.maxlen) * 0.2
+        sd[f"{o}.q_layer.weight"], sd[f"{o}.q_layer.bias"] = _fanin((h, h), 0.1), torch.zeros(h)
+        sd[f"{o}.k_layer.weight"] = _fanin((h, h), 0.2)
+        sd[f"{o}.v_layer.weight"] = _fanin((h, h), 1.0 * s_att)
+        sd[f"{o}.proj_layer.weight"], sd[f"{o}.proj_layer.bias"] = _fanin((h, h), 1.0 * s_att), torch.zeros(h)
+        sd[f"{o}.r_layer.weight"], sd[f"{o}.r_layer.bias"] = _fanin((NBASIS * cfg.heads, h), 0.1), torch.zeros(NBASIS * cfg.heads)
+    sd["lastlayer.norm.weight"], sd["lastlayer.norm.bias"] = torch.ones(h), torch.zeros(h)
+    sd["lastlayer.layer.weight"] = _fanin((h, h), 1.0)
+    sd["final_ln.weight"], sd["final_ln.bias"] = torch.ones(h), torch.zeros(h)
+    return sd
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernel-side weight layouts
+# ---------------------------------------------------------------------------------------------------------------
+def _fold_conv(W, gamma, beta):
+    """GroupNorm(1) -> conv3x3(pad 1) fold:
+    conv(GN(x))[o,p] = rstd*conv_{W*gamma}(x)[o,p] - rstd*mean*S1[cls(p)][o] + S2[cls(p)][o].
+    S1 is summed from the bf16-ROUNDED weights (the ones the tensor cores multiply) so the mean term cancels exactly."""
+    Wg = (W * gamma[None, :, None, None]).permute(0, 2, 3, 1).contiguous()  # [Cout, ky, kx, Cin]
+    Wb = Wg.to(BF16)
+    tg = Wb.double().sum(-1)                                                # [Cout, 3, 3]
+    tb = (W.double() * beta.double()[None, :, None, None]).sum(1)           # [Cout, 3, 3]
+    valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}                            # row/col class -> in-bounds taps
+    S1 = torch.empty(9, W.shape[0], dtype=torch.float64, device=W.device)
+    S2 = torch.empty_like(S1)
+    for cy in range(3):
+        for cx in range(3):
+            S1[cy * 3 + cx] = tg[:, valid[cy]][:, :, valid[cx]].sum((1, 2))
+            S2[cy * 3 + cx] = tb[:, valid[cy]][:, :, valid[cx]].sum((1, 2))
+    return Wb.reshape(W.shape[0], -1).contiguous(), S1.float().contiguous(), S2.float().contiguous()
+
+
+def _fold_linear(W, gamma=None, beta=None, bias=None):
+    """[LayerNorm ->] Linear fold: out = rstd*(x @ (W*gamma)^T) - rstd*mean*S1 + S2, S2 = W @ beta (+ bias)."""
+    Wg = W if gamma is None else W * gamma[None, :]
+    Wb = Wg.to(BF16).contiguous()
+    S1 = Wb.double().sum(1).float().contiguous() if gamma is not None else None
+    S2 = None
+    if beta is not None:
+        S2 = (W.double() @ beta.double())
+    if bias is not None:
+        S2 = bias.double() if S2 is None else S2 + bias.double()
+    return Wb, S1, (S2.float().contiguous() if S2 is not None else None)
+
+
+class _Prepared:
+    """Device-side, kernel-layout copy of the parameters of one MinecraftPolicy (+ optional heads)."""
+
+    def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], prefix: str = ""):
+        g = lambda k: sd[prefix + k].detach()
+        p = "img_process.cnn"
+        self.stacks = []
+        for i, c in enumerate(cfg.chans):
+            s = f"{p}.stacks.{i}"
+            st = {}
+            if i == 0 and not cfg.first_conv_norm:
+                w = g(f"{s}.firstconv.layer.weight")  # [C0, 3, ky, kx] -> [C0][ky][kx][c] / 255 (lib/policy.py:44)
+                st["fc_w"] = (w.double().permute(0, 2, 3, 1).reshape(c, 27) / 255.0).float().contiguous()
+                st["fc_b"] = g(f"{s}.firstconv.layer.bias").float().contiguous()
+            else:
+                st["first"] = _fold_conv(g(f"{s}.firstconv.layer.weight"), g(f"{s}.firstconv.norm.weight"), g(f"{s}.firstconv.norm.bias"))
+            st["n_g"], st["n_b"] = g(f"{s}.n.weight").float().contiguous(), g(f"{s}.n.bias").float().contiguous()
+            st["convs"] = []
+            for j in range(2):
+                for k in range(2):
+                    q = f"{s}.blocks.{j}.conv{k}"
+                    st["convs"].append(_fold_conv(g(f"{q}.layer.weight"), g(f"{q}.norm.weight"), g(f"{q}.norm.bias")))
+            self.stacks.append(st)
+        C2 = cfg.chans[-1]
+        Hf, Wf = cfg.final_hw
+        # dense: reference flatten order is c*H*W + h*W + w (lib/impala_cnn.py:192-193); ours is NHWC
+        perm = lambda v: v.reshape(*v.shape[:-1], C2, Hf, Wf).movedim(-3, -1).reshape(*v.shape[:-1], -1)
+        self.dense = _fold_linear(perm(g(f"{p}.dense.layer.weight")), perm(g(f"{p}.dense.norm.weight")), perm(g(f"{p}.dense.norm.bias")))
+        self.linear = _fold_linear(g("img_process.linear.layer.weight"), g("img_process.linear.norm.weight"), g("img_process.linear.norm.bias"))
+        self.layers = []
+        for l in range(cfg.n_layers):
+            b = f"recurrent_layer.blocks.{l}"
+            o = f"{b}.r.orc_block"
+            L = {}
+            L["ln_g"], L["ln_b"] = g(f"{b}.pre_r_ln.weight").float().contiguous(), g(f"{b}.pre_r_ln.bias").float().contiguous()
+            L["q"] = _fold_linear(g(f"{o}.q_layer.weight"), bias=g(f"{o}.q_layer.bias"))
+            L["k"] = _fold_linear(g(f"{o}.k_layer.weight"))
+            L["v"] = _fold_linear(g(f"{o}.v_layer.weight"))
+            L["r"] = _fold_linear(g(f"{o}.r_layer.weight"), bias=g(f"{o}.r_layer.bias"))
+            L["b_nd"] = g(f"{o}.b_nd").float().contiguous()
+            L["proj"] = _fold_linear(g(f"{o}.proj_layer.weight"), bias=g(f"{o}.proj_layer.bias"))
+            L["mlp0"] = _fold_linear(g(f"{b}.mlp0.layer.weight"), g(f"{b}.mlp0.norm.weight"), g(f"{b}.mlp0.norm.bias"))
+            L["mlp1"] = _fold_linear(g(f"{b}.mlp1.layer.weight"), bias=g(f"{b}.mlp1.layer.bias"))
+            self.layers.append(L)
+        self.last = _fold_linear(g("lastlayer.layer.weight"), g("lastlayer.norm.weight"), g("lastlayer.norm.bias"))
+        self.fin_g, self.fin_b = g("final_ln.weight").float().contiguous(), g("final_ln.bias").float().contiguous()
+
+
+def _fingerprint(module: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MinecraftPolicy
+# ---------------------------------------------------------------------------------------------------------------
+class MinecraftPolicy(nn.Module):
+    """lib/policy.py:83-224.  `forward(ob, state_in, context)` -> ((pi_latent, vf_latent), state_out)."""
+
+    cnn_chunk_frames = 2048  # frames per CNN pass (bounds the activation workspace: ~5 MiB/frame at 2x width)
+
+    def __init__(self, **policy_kwargs):
+        super().__init__()
+        self.cfg = NetConfig(**policy_kwargs)
+        self.hidsize = self.cfg.hidsize
+        self.single_output = self.cfg.single_output
+        for name, t in _net_schema(self.cfg).items():
+            _set(self, name, t)
+        self._prep = None
+        self._prep_fp = None
+        self.debug_taps = None  # set to a dict to capture intermediate activations (tests)
+
+    def output_latent_size(self):
+        return self.hidsize
+
+    def initial_state(self, batchsize):
+        """lib/policy.py:220-224 -> lib/xf.py:393-397: zeros on the module's device; state_mask None."""
+        dev = self.final_ln.weight.device
+        mk = lambda: torch.zeros((batchsize, self.cfg.maxlen, self.hidsize), dtype=F32, device=dev)
+        return [(None, (mk(), mk())) for _ in range(self.cfg.n_layers)]
+
+    # -- weights -------------------------------------------------------------------------------------------
+    def prepared(self) -> _Prepared:
+        fp = _fingerprint(self)
+        if self._prep is None or fp != self._prep_fp:
+            with torch.no_grad():
+                self._prep = _Prepared(self.cfg, dict(self.named_parameters()))
+            self._prep_fp = fp
+        return self._prep
+
+    def _tap(self, name, t):
+        if self.debug_taps is not None:
+            self.debug_taps[name] = t
+
+    # -- CNN -----------------------------------------------------------------------------------------------
+    def _conv(self, x, mr, fold, H, W, Cin, Cout, relu=1, residual=None, want_stats=True):
+        """One GroupNorm(1)->conv3x3->ReLU[+residual] layer on bf16 NHWC `x` [F,H,W,Cin] whose per-frame stats are `mr`."""
+        Wb, S1, S2 = fold
+        F_ = x.shape[0]
+        M = F_ * H * W
+        out = torch.empty((F_, H, W, Cout), dtype=BF16, device=x.device)
+        part, mode, P, npg = None, 0, ops.gemm_stat_parts(Cout), 0
+        if want_stats:
+            mode = 2 if (H * W) % 32 == 0 else 1
+            rows = (M + 31) // 32 if mode == 2 else M
+            part = torch.empty((rows, P, 2), dtype=F32, device=x.device)
+            npg = (H * W // 32 if mode == 2 else H * W) * P
+        ops.gemm(x, Wb, out, M, Cout, 9 * Cin, conv=(H, W, Cin), mr=mr, rows_per_group=H * W, S1=S1, S2=S2, relu=relu,
+                 residual=residual, ld_out=Cout, stat_part=part, stat_mode=mode)
+        mr_out = ops.stats_finalize(part, F_, npg, H * W * Cout) if want_stats else None
+        return out, mr_out
+
+    def _cnn_chunk(self, img, prep: _Prepared, pfx="img_process.cnn"):
+        """lib/impala_cnn.py:187-195 for a chunk of frames; returns (x [F, Hf, Wf, C2] bf16, per-frame stats)."""
+        cfg = self.cfg
+        H, W = cfg.img_shape[0], cfg.img_shape[1]
+        x, mr, cin = None, None, 3
+        for i, c in enumerate(cfg.chans):
+            st = prep.stacks[i]
+            if i == 0 and "fc_w" in st:
+                y1, mr1 = ops.firstconv_pool(img, st["fc_w"], st["fc_b"], c)
+            else:
+                full, _ = self._conv(x, mr, st["first"], H, W, cin, c, want_stats=False)
+                y1, mr1 = ops.maxpool3s2(full)
+                del full
+            H, W = H // 2, W // 2
+            self._tap(f"{pfx}.stacks.{i}.pool", y1)
+            # post-pool GroupNorm `n` (lib/impala_cnn.py:119): materialised because it is the residual stream
+            x, _, mr = ops.affine_norm(y1, mr1, st["n_g"], st["n_b"], rows_per_group=H * W, want_stats=True)
+            del y1
+            self._tap(f"{pfx}.stacks.{i}.n", x)
+            for j in range(2):
+                hmid, mrh = self._conv(x, mr, st["convs"][2 * j], H, W, c, c)
+                self._tap(f"{pfx}.stacks.{i}.blocks.{j}.conv0", hmid)
+                x, mr = self._conv(hmid, mrh, st["convs"][2 * j + 1], H, W, c, c, residual=x)
+                self._tap(f"{pfx}.stacks.{i}.blocks.{j}", x)
+            cin = c
+        return x, mr
+
+    # -- transformer -----------------------------------------------------------------------------------------
+    def _linear(self, x, fold, N, *, mr=None, relu=0, residual=None, out=None, out_dtype=BF16, seg=None, want_stats=False,
+                out_scale=1.0, ld_out=None):
+        Wb, S1, S2 = fold
+        M, K = x.shape[0], x.shape[1]
+        if out is None:
+            out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        part, P = None, ops.gemm_stat_parts(N)
+        if want_stats:
+            part = torch.empty((M, P, 2), dtype=F32, device=x.device)
+        ops.gemm(x, Wb, out, M, N, K, mr=mr, rows_per_group=1, S1=S1 if mr is not None else None, S2=S2, relu=relu,
+                 residual=residual, seg=seg, stat_part=part, stat_mode=1 if want_stats else 0, out_scale=out_scale, ld_out=ld_out)
+        mr_out = ops.stats_finalize(part, M, P, N) if want_stats else None
+        return out, mr_out
+
+    def _block(self, l, x, mr_x, first_u8, state, B, t, prep: _Prepared, last: bool):
+        """lib/util.py:193-211: x_hat = LN(x); y = x_hat + Proj(Attn(x_hat)); z = y + mlp1(relu(mlp0(LN(y))))."""
+        cfg, L = self.cfg, prep.layers[l]
+        h, heads, maxlen = cfg.hidsize, cfg.heads, cfg.maxlen
+        causal = cfg.mask_style == "clipped_causal"
+        state_mask, (mem_k, mem_v) = state
+        xhat, _, _ = ops.affine_norm(x, mr_x, L["ln_g"], L["ln_b"], rows_per_group=1)
+        T = maxlen + t
+        full_k = torch.empty((B, T, h), dtype=BF16, device=x.device)
+        full_v = torch.empty((B, T, h), dtype=BF16, device=x.device)
+        if maxlen > 0:
+            if mem_k.shape != (B, maxlen, h):
+                raise AssertionError(f"KV memory shape {tuple(mem_k.shape)} != {(B, maxlen, h)}")
+            ops.copy_rows(mem_k, 0, full_k, 0, maxlen)  # lib/xf.py:378-379  full = cat(prev, new)
+            ops.copy_rows(mem_v, 0, full_v, 0, maxlen)
+        q, _ = self._linear(xhat, L["q"], h)
+        self._linear(xhat, L["k"], h, out=full_k, seg=(t, T, maxlen), ld_out=h)
+        self._linear(xhat, L["v"], h, out=full_v, seg=(t, T, maxlen), ld_out=h)
+        R = None
+        if causal:
+            R, _ = self._linear(xhat, L["r"], NBASIS * heads, out_dtype=F32)
+        smask_u8 = state_mask.contiguous().view(torch.uint8) if state_mask is not None else None
+        a = ops.attention(q, full_k, full_v, R, L["b_nd"], first_u8, smask_u8, B, t, maxlen, heads, causal=causal)
+        # new state (lib/xf.py:380-381: last `maxlen` rows of full; lib/masked_attention.py:86-92)
+        new_k = torch.empty((B, maxlen, h), dtype=F32, device=x.device)
+        new_v = torch.empty((B, maxlen, h), dtype=F32, device=x.device)
+        ops.copy_rows(full_k, T - maxlen, new_k, 0, maxlen)
+        ops.copy_rows(full_v, T - maxlen, new_v, 0, maxlen)
+        new_mask = ops.state_mask_update(smask_u8, first_u8, t, maxlen) if causal else state_mask
+        y, mr_y = self._linear(a, L["proj"], h, residual=xhat, want_stats=True)
+        self._tap(f"recurrent_layer.blocks.{l}.attn", y)
+        hmid, _ = self._linear(y, L["mlp0"], h * cfg.pointwise_ratio, mr=mr_y, relu=1)
+        # the F.relu of lib/policy.py:211 is fused into the last block's epilogue (relu after the residual add)
+        z, mr_z = self._linear(hmid, L["mlp1"], h, residual=y, relu=2 if last else 0, want_stats=True)
+        if not last:
+            self._tap(f"recurrent_layer.blocks.{l}", z)
+        return z, mr_z, (new_mask, (new_k, new_v))
+
+    # -- whole net -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _forward_impl(self, img, first, state_in, use_lastlayer=True):
+        cfg = self.cfg
+        ops.require_cuda(img)
+        if img.dtype != torch.uint8:
+            raise TypeError("ob['img'] must be uint8 (B,T,H,W,3) as in the reference (lib/policy.py:39-45)")
+        B, t = img.shape[:2]
+        assert tuple(img.shape[2:]) == cfg.img_shape, f"img shape {tuple(img.shape[2:])} != {cfg.img_shape}"
+        assert len(state_in) == cfg.n_layers, \
+            f"Length of state {len(state_in)} did not match length of blocks {cfg.n_layers}"  # lib/util.py:117-119
+        prep = self.prepared()
+        N = B * t
+        frames = img.reshape(N, *cfg.img_shape).contiguous()
+        first_u8 = first.to(device=img.device, dtype=torch.bool).contiguous().view(torch.uint8)
+        Hf, Wf = cfg.final_hw
+        C2 = cfg.chans[-1]
+        # ---- ImpalaCNN + dense, in frame chunks
+        xd = torch.empty((N, cfg.cnn_outsize), dtype=BF16, device=img.device)
+        Pd = ops.gemm_stat_parts(cfg.cnn_outsize)
+        part_d = torch.empty((N, Pd, 2), dtype=F32, device=img.device)
+        Wd, S1d, S2d = prep.dense
+        for f0 in range(0, N, self.cnn_chunk_frames):
+            F_ = min(self.cnn_chunk_frames, N - f0)
+            x, mr = self._cnn_chunk(frames[f0:f0 + F_], prep)
+            ops.gemm(x.view(F_, Hf * Wf * C2), Wd, xd[f0:f0 + F_], F_, cfg.cnn_outsize, Hf * Wf * C2, mr=mr, rows_per_group=1,
+                     S1=S1d, S2=S2d, relu=1, stat_part=part_d[f0:f0 + F_], stat_mode=1)
+            del x, mr
+        mr_d = ops.stats_finalize(part_d, N, Pd, cfg.cnn_outsize)
+        self._tap("img_process.cnn.dense", xd)
+        x, mr_x = self._linear(xd, prep.linear, cfg.hidsize, mr=mr_d, relu=1, want_stats=True)
+        self._tap("img_process", x)
+        # ---- transformer
+        state_out = []
+        for l in range(cfg.n_layers):
+            x, mr_x, s = self._block(l, x, mr_x, first_u8, state_in[l], B, t, prep, last=(l == cfg.n_layers - 1))
+            state_out.append(s)
+        # x is relu(recurrent output) here
+        if use_lastlayer:
+            x, mr_x = self._linear(x, prep.last, cfg.hidsize, mr=mr_x, relu=1, want_stats=True)
+        lat_bf16, lat_f32, _ = ops.affine_norm(x, mr_x, prep.fin_g, prep.fin_b, rows_per_group=1, want_f32=True)
+        return lat_bf16, lat_f32.view(B, t, cfg.hidsize), state_out
+
+    def forward(self, ob, state_in, context):
+        """lib/policy.py:193-218."""
+        first = context["first"]
+        _, latent, state_out = self._forward_impl(ob["img"], first, state_in)
+        if self.single_output:
+            return latent, state_out
+        return (latent, latent), state_out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# heads + MinecraftAgentPolicy
+# ---------------------------------------------------------------------------------------------------------------
+class MinecraftAgentPolicy(nn.Module):
+    """lib/policy.py:227-339."""
+
+    def __init__(self, action_space, policy_kwargs, pi_head_kwargs):
+        super().__init__()
+        self.net = MinecraftPolicy(**policy_kwargs)
+        self.action_space = action_space
+        self.temperature = float(pi_head_kwargs.get("temperature", 1.0))
+        h = self.net.output_latent_size()
+        # value head: lib/scaled_mse_head.py:24 + lib/normalize_ewma.py:18-20
+        w, b = _default_linear(1, h)
+        _set(self, "value_head.linear.weight", w)
+        _set(self, "value_head.linear.bias", b)
+        _set(self, "value_head.normalizer.running_mean", torch.zeros(1), requires_grad=False)
+        _set(self, "value_head.normalizer.running_mean_sq", torch.zeros(1), requires_grad=False)
+        _set(self, "value_head.normalizer.debiasing_term", torch.tensor(0.0), requires_grad=False)
+        # pi head: lib/action_head.py:263-275 -> one CategoricalActionHead per Discrete TensorType, in dict order
+        self.head_specs = OrderedDict()
+        for name, space in action_space.items():
+            n = space.eltype.n
+            shape = tuple(space.shape)
+            cnt = 1
+            for s_ in shape:
+                cnt *= s_
+            w, b = _default_linear(cnt * n, h)
+            _set(self, f"pi_head.{name}.linear_layer.weight", w)
+            _set(self, f"pi_head.{name}.linear_layer.bias", b)
+            self.head_specs[name] = (shape, n)
+        self._hprep = None
+        self._hprep_fp = None
+
+    # -- API ------------------------------------------------------------------------------------------------
+    def initial_state(self, batch_size: int):
+        return self.net.initial_state(batch_size)
+
+    def _heads_prepared(self):
+        params = [p for n, p in self.named_parameters() if not n.startswith("net.")]
+        fp = tuple((p.data_ptr(), p._version) for p in params)
+        if self._hprep is None or fp != self._hprep_fp:
+            with torch.no_grad():
+                ws, bs, cols, c0 = [], [], OrderedDict(), 0
+                for name, (shape, n) in self.head_specs.items():
+                    lin = getattr(self.pi_head, name).linear_layer
+                    ws.append(lin.weight.detach())
+                    bs.append(lin.bias.detach())
+                    cols[name] = (c0, lin.weight.shape[0])
+                    c0 += lin.weight.shape[0]
+                self._hprep = dict(pi=_fold_linear(torch.cat(ws, 0), bias=torch.cat(bs, 0)), cols=cols, ntot=c0,
+                                   v=_fold_linear(self.value_head.linear.weight.detach(), bias=self.value_head.linear.bias.detach()))
+            self._hprep_fp = fp
+        return self._hprep
+
+    @torch.no_grad()
+    def _heads(self, lat_bf16, B, t, mask=None):
+        """lib/action_head.py:163-174 for every head + lib/scaled_mse_head.py:34-35."""
+        hp = self._heads_prepared()
+        N = lat_bf16.shape[0]
+        ntot = hp["ntot"]
+        ld = (ntot + 7) // 8 * 8
+        raw = torch.empty((N, ld), dtype=F32, device=lat_bf16.device)
+        self.net._linear(lat_bf16, hp["pi"], ntot, out=raw, out_scale=1.0 / self.temperature, ld_out=ld)
+        pd = OrderedDict()
+        for name, (shape, n) in self.head_specs.items():
+            c0, width = hp["cols"][name]
+            if mask is not None and mask.get(name) is not None:
+                raise NotImplementedError("vpt_b200: logit masks (obs['mask']) are not supported yet")
+            cnt = width // n
+            if cnt == 1:
+                lp = ops.log_softmax(raw, c0, n)
+            else:  # several sub-actions per head (IDM): softmax over each group of n columns
+                lp = torch.cat([ops.log_softmax(raw, c0 + i * n, n) for i in range(cnt)], dim=1)
+            pd[name] = lp.view(B, t, *shape, n)
+        vpred, _ = self.net._linear(lat_bf16, hp["v"], 1, out_dtype=F32)
+        return pd, vpred.view(B, t, 1)
+
+    def forward(self, obs, first: torch.Tensor, state_in):
+        """lib/policy.py:252-269 -> ((pi_logits, vpred, None), state_out)."""
+        if isinstance(obs, dict):
+            obs = obs.copy()
+            mask = obs.pop("mask", None)
+        else:
+            mask = None
+        lat_bf16, _, state_out = self.net._forward_impl(obs["img"], first, state_in)
+        B, t = obs["img"].shape[:2]
+        pi_logits, vpred = self._heads(lat_bf16, B, t, mask)
+        return (pi_logits, vpred, None), state_out
+
+    # -- distribution helpers (lib/action_head.py:176-220, 250-260) ---------------------------------------------
+    def sample(self, pd, deterministic: bool = False):
+        """DictActionHead.sample: per head in dict order; `torch.rand_like` supplies the uniforms so the Philox stream
+        is consumed exactly like the reference's (lib/action_head.py:200)."""
+        ac = OrderedDict()
+        for name in self.head_specs:
+            lg = pd[name].contiguous()
+            u = None if deterministic else torch.rand_like(lg)
+            ac[name] = ops.gumbel_argmax(lg, u)
+        return ac
+
+    def logprob(self, ac, pd):
+        tot = None
+        for name, (shape, n) in self.head_specs.items():
+            lg = pd[name].contiguous()
+            lp = ops.gather_logprob(lg, ac[name].to(torch.int64))
+            for _ in shape:
+                lp = lp.sum(dim=-1)
+            tot = lp if tot is None else tot + lp
+        return tot
+
+    def denormalize(self, v):
+        """lib/normalize_ewma.py:31-35,57-60 (a 3-scalar affine map; host-side glue)."""
+        nz = self.value_head.normalizer
+        deb = nz.debiasing_term.clamp(min=1e-5)
+        mean = nz.running_mean / deb
+        var = (nz.running_mean_sq / deb - mean ** 2).clamp(min=1e-2)
+        return v * torch.sqrt(var)[None, None] + mean[None, None]
+
+    def get_logprob_of_action(self, pd, action):
+        """lib/policy.py:271-279."""
+        ac = {k: v.unsqueeze(1) for k, v in action.items()}
+        log_prob = self.logprob(ac, pd)
+        assert not torch.isnan(log_prob).any()
+        return log_prob[:, 0]
+
+    def get_kl_of_action_dists(self, pd1, pd2):
+        """lib/policy.py:281-285 / lib/action_head.py:209-220 (diagnostic, not on the hot path: torch ops)."""
+        tot = 0
+        for name, (shape, n) in self.head_specs.items():
+            kl = (torch.exp(pd1[name]) * (pd1[name] - pd2[name])).sum(-1, keepdim=True)
+            for _ in shape:
+                kl = kl.sum(dim=-2)
+            tot = tot + kl
+        return tot
+
+    def get_output_for_observation(self, obs, state_in, first):
+        """lib/policy.py:287-305."""
+        obs = {k: v.unsqueeze(1) for k, v in obs.items()}
+        first = first.unsqueeze(1)
+        (pd, vpred, _), state_out = self(obs=obs, first=first, state_in=state_in)
+        return pd, self.denormalize(vpred)[:, 0], state_out
+
+    @torch.no_grad()
+    def act(self, obs, first, state_in, stochastic: bool = True, taken_action=None, return_pd=False):
+        """lib/policy.py:307-328."""
+        obs = {k: v.unsqueeze(1) for k, v in obs.items()}
+        first = first.unsqueeze(1)
+        (pd, vpred, _), state_out = self(obs=obs, first=first, state_in=state_in)
+        if taken_action is None:
+            ac = self.sample(pd, deterministic=not stochastic)
+        else:
+            ac = {k: v.unsqueeze(1) for k, v in taken_action.items()}
+        log_prob = self.logprob(ac, pd)
+        assert not torch.isnan(log_prob).any()
+        result = {"log_prob": log_prob[:, 0], "vpred": self.denormalize(vpred)[:, 0]}
+        if return_pd:
+            result["pd"] = {k: v[:, 0] for k, v in pd.items()}
+        ac = {k: v[:, 0] for k, v in ac.items()}
+        return ac, state_out, result
+
+    @torch.no_grad()
+    def v(self, obs, first, state_in):
+        """lib/policy.py:330-339."""
+        obs = {k: v.unsqueeze(1) for k, v in obs.items()}
+        first = first.unsqueeze(1)
+        (pd, vpred, _), state_out = self(obs=obs, first=first, state_in=state_in)
+        return self.denormalize(vpred)[:, 0]
