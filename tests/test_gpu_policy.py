@@ -1,0 +1,113 @@
+"""GPU: the drop-in policy (CUDA path through the C ABI) against the oracle on the same seeded inputs.
+Tolerance (BASELINE.json north_star): 1e-2 relative on the log-prob outputs for the bf16 path."""
+import pytest
+import torch
+
+import vpt_b200
+import vpt_oracle as O
+from common import l2_err, make_policy, rel_err, run_chunks, small_kwargs
+from video_pre_training_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL_BF16 = 1e-2
+
+
+def _check(res, tag):
+    for ci, r in enumerate(res):
+        for k in r["pd"]:
+            got = r["pd"][k].float().cpu()
+            assert got.shape == r["pd_o"][k].shape and torch.isfinite(got).all()
+            e = rel_err(got, r["pd_o"][k])
+            assert e < RTOL_BF16, f"{tag} chunk {ci} head {k}: max rel err {e:.4g} (l2 {l2_err(got, r['pd_o'][k]):.3g})"
+        assert (r["v"].cpu() - r["v_o"]).abs().max() < 0.1
+        for (m, (k_, v_)), (mo, (ko, vo)) in zip(r["st"], r["st_o"]):
+            assert torch.equal(m.cpu(), mo)
+            assert l2_err(k_.cpu(), ko) < 5e-2 and l2_err(v_.cpu(), vo) < 5e-2
+
+
+def _layer_report(r):
+    rows = []
+    for k, t in r["taps"].items():
+        ko = "net." + k
+        if r["taps_o"] and ko in r["taps_o"]:
+            ref = r["taps_o"][ko]
+            tt = t.float().cpu()
+            if tt.dim() == 4:
+                tt = tt.permute(0, 3, 1, 2)
+            rows.append(f"{k}: {l2_err(tt.reshape(ref.shape), ref):.3g}")
+    return "; ".join(rows)
+
+
+@pytest.mark.parametrize("pert", [False, True])
+def test_small_config_multi_chunk(pert):
+    pol, sd, cfg = make_policy(small_kwargs(), pert=pert)
+    pol = pol.to(DEV)
+    res = run_chunks(pol, sd, cfg, B=3, chunks=[8, 3, 8, 1], dev=DEV, first_at=(2, 1), taps=True)
+    nat.device_check()
+    print("per-layer rel l2 err (chunk 0):", _layer_report(res[0]))
+    _check(res, f"small pert={pert}")
+
+
+def test_fullsize_frames_1x():
+    """128x128 frames through the 1x model (B=2, T=6, two chunks)."""
+    kw = vpt_b200.policy_kwargs("1x", n_recurrence_layers=2)
+    pol, sd, cfg = make_policy(kw, pert=True)
+    pol = pol.to(DEV)
+    res = run_chunks(pol, sd, cfg, B=2, chunks=[4, 2], dev=DEV, taps=True)
+    nat.device_check()
+    print("per-layer rel l2 err (chunk 0):", _layer_report(res[0]))
+    _check(res, "1x 128px")
+
+
+def test_fullsize_frames_2x_single_step():
+    """Config C1 shape at the agent.py default width: one 128x128 frame, B=1, T=1."""
+    kw = vpt_b200.policy_kwargs("2x")
+    pol, sd, cfg = make_policy(kw, pert=False)
+    pol = pol.to(DEV)
+    res = run_chunks(pol, sd, cfg, B=1, chunks=[1, 1], dev=DEV)
+    nat.device_check()
+    _check(res, "2x B=1 T=1")
+
+
+def test_act_sampling_bit_exact_given_logits():
+    pol, sd, cfg = make_policy(small_kwargs())
+    pol = pol.to(DEV)
+    B = 4
+    img = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8, device=DEV)
+    first = torch.zeros(B, dtype=torch.bool, device=DEV)
+    torch.manual_seed(1234)
+    ac, st, res = pol.act({"img": img}, first, pol.initial_state(B), return_pd=True)
+    # the reference's sampler (torch ops, lib/action_head.py:195-207) on the SAME logits with the SAME Philox stream
+    torch.manual_seed(1234)
+    for name in ("camera", "buttons"):
+        lg = res["pd"][name].unsqueeze(1).contiguous()
+        u = torch.rand_like(lg)
+        u[u == 1.0] = 0.999
+        ref = torch.argmax(lg - torch.log(-torch.log(u)), dim=-1)[:, 0]
+        assert torch.equal(ref, ac[name]), name
+    lp = sum(res["pd"][k].gather(-1, ac[k].unsqueeze(-1)).squeeze(-1).sum(-1) for k in ("camera", "buttons"))
+    assert torch.allclose(lp, res["log_prob"])
+    nat.device_check()
+
+
+def test_chunk_invariance_and_reset_on_gpu():
+    """Size-independent properties: chunking does not change the logits; first=True == fresh state."""
+    pol, sd, cfg = make_policy(small_kwargs())
+    pol = pol.to(DEV)
+    B, N = 2, 16
+    img = torch.randint(0, 256, (B, N, 32, 32, 3), dtype=torch.uint8, device=DEV)
+    outs = []
+    for cs in (4, 16):
+        st, acc = pol.initial_state(B), []
+        for t0 in range(0, N, cs):
+            (pd, _, _), st = pol({"img": img[:, t0:t0 + cs]}, torch.zeros(B, cs, dtype=torch.bool, device=DEV), st)
+            acc.append(pd["camera"])
+        outs.append(torch.cat(acc, 1))
+    assert (outs[0] - outs[1]).abs().max() < 3e-2
+    first = torch.zeros(B, 8, dtype=torch.bool, device=DEV)
+    first[:, 0] = True
+    (pd1, _, _), _ = pol({"img": img[:, 8:]}, first, st)
+    (pd2, _, _), _ = pol({"img": img[:, 8:]}, torch.zeros(B, 8, dtype=torch.bool, device=DEV), pol.initial_state(B))
+    assert torch.equal(pd1["buttons"], pd2["buttons"])
+    nat.device_check()
