@@ -70,7 +70,7 @@ def fanin_conv(x: Tensor, sd: Dict[str, Tensor], p: str) -> Tensor:
     if p + ".norm.weight" in sd:
         x = F.group_norm(x, 1, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-5)
     x = F.conv2d(x, sd[p + ".layer.weight"], sd.get(p + ".layer.bias"), padding=1)
-    return F.relu(x)
+    return F.relu(x, inplace=True)  # in place like the reference (lib/util.py:81); also what keeps the CPU baseline fair
 
 
 def fanin_linear(x: Tensor, sd: Dict[str, Tensor], p: str, relu: bool = True) -> Tensor:
@@ -78,7 +78,7 @@ def fanin_linear(x: Tensor, sd: Dict[str, Tensor], p: str, relu: bool = True) ->
     if p + ".norm.weight" in sd:
         x = F.layer_norm(x, (x.shape[-1],), sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-5)
     x = F.linear(x, sd[p + ".layer.weight"], sd.get(p + ".layer.bias"))
-    return F.relu(x) if relu else x
+    return F.relu(x, inplace=True) if relu else x
 
 
 def cnn_basic_block(x: Tensor, sd, p: str, taps=None) -> Tensor:

@@ -9,6 +9,15 @@ from . import _native as nat
 BF16, F32 = torch.bfloat16, torch.float32
 
 
+LAUNCHES = 0        # kernels launched through this module since import (bench.py reports the per-step delta)
+GEMM_PROFILE = None  # set to a list to record (start_event, end_event, flops, tag) around every GEMM/conv launch
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -45,7 +54,15 @@ def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, 
     if seg is not None:
         a.seg_len, a.seg_stride, a.seg_off = seg
     a.stat_part, a.stat_mode = _p(stat_part), stat_mode
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     nat.check(nat.lib().vpt_gemm_bf16(C.byref(a), _stream()), "vpt_gemm_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K, "conv" if conv is not None else "linear", (M, N, K)))
+    _count()
     return out
 
 
@@ -56,6 +73,7 @@ def gemm_stat_parts(N):
 def stats_finalize(part, G, n_per_group, count, eps=1e-5):
     mr = torch.empty((G, 2), dtype=F32, device=part.device)
     nat.check(nat.lib().vpt_stats_finalize(_p(part), _p(mr), G, n_per_group, float(count), eps, _stream()), "vpt_stats_finalize")
+    _count()
     return mr
 
 
@@ -67,6 +85,7 @@ def firstconv_pool(img, w, bias, C0):
     P = nat.lib().vpt_firstconv_stat_parts(H, W)
     part = torch.empty((F_, P, 2), dtype=F32, device=img.device)
     nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, _stream()), "vpt_firstconv_pool")
+    _count()
     return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * C0)
 
 
@@ -78,6 +97,7 @@ def maxpool3s2(x):
     P = nat.lib().vpt_pool_stat_parts(H, W, Cc)
     part = torch.empty((F_, P, 2), dtype=F32, device=x.device)
     nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), F_, H, W, Cc, _stream()), "vpt_maxpool3s2")
+    _count()
     return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * Cc)
 
 
@@ -95,6 +115,7 @@ def affine_norm(x, mr, gamma, beta, rows_per_group, want_stats=False, want_f32=F
         part = torch.empty((G, P, 2), dtype=F32, device=x.device)
     nat.check(nat.lib().vpt_affine_norm(_p(x), _p(mr), _p(gamma), _p(beta), _p(out), _p(out32), _p(part), M, Cc, rows_per_group,
                                         _stream()), "vpt_affine_norm")
+    _count()
     mr_out = stats_finalize(part, G, P, rows_per_group * Cc) if want_stats else None
     return out, out32, mr_out
 
@@ -108,6 +129,7 @@ def copy_rows(src, src_off, dst, dst_off, rows):
     nat.check(nat.lib().vpt_copy_rows(_p(src), int(src.dtype == F32), src.stride(0), src.stride(1), src_off, _p(dst),
                                       int(dst.dtype == F32), dst.stride(0), dst.stride(1), dst_off, B, rows, Cc, _stream()),
               "vpt_copy_rows")
+    _count()
 
 
 def state_mask_update(mask_in, first_u8, t, maxlen):
@@ -117,6 +139,7 @@ def state_mask_update(mask_in, first_u8, t, maxlen):
     if maxlen > 0:
         nat.check(nat.lib().vpt_state_mask_update(_p(mask_in), _p(first_u8), first_u8.stride(0), _p(out), B, t, maxlen, _stream()),
                   "vpt_state_mask_update")
+    _count()
     return out
 
 
@@ -127,6 +150,7 @@ def attention(Q, Kf, Vf, R, b_nd, first_u8, smask, B, t, maxlen, heads, causal=T
     nat.check(nat.lib().vpt_attention(_p(Q), _p(Kf), _p(Vf), _p(R), R.stride(-2) if R is not None else 0, _p(b_nd),
                                       _p(first_u8), first_u8.stride(0) if first_u8 is not None else 0, _p(smask), _p(out), B, t,
                                       maxlen, heads, nbasis, int(causal), _stream()), "vpt_attention")
+    _count()
     return out
 
 
@@ -135,6 +159,7 @@ def log_softmax(raw, col0, n):
     rows = raw.shape[0]
     out = torch.empty((rows, n), dtype=F32, device=raw.device)
     nat.check(nat.lib().vpt_log_softmax(_p(raw), raw.stride(0), col0, n, _p(out), rows, _stream()), "vpt_log_softmax")
+    _count()
     return out
 
 
@@ -146,6 +171,7 @@ def gumbel_argmax(logits, u=None):
     rows = logits.numel() // n
     idx = torch.empty(logits.shape[:-1], dtype=torch.int64, device=logits.device)
     nat.check(nat.lib().vpt_gumbel_argmax(_p(logits), _p(u), _p(idx), rows, n, _stream()), "vpt_gumbel_argmax")
+    _count()
     return idx
 
 
@@ -158,4 +184,5 @@ def gather_logprob(logits, idx, lp=None):
     if lp is None:
         lp = torch.empty(logits.shape[:-1], dtype=F32, device=logits.device)
     nat.check(nat.lib().vpt_gather_logprob(_p(logits), _p(idx), _p(lp), rows, n, int(acc), _stream()), "vpt_gather_logprob")
+    _count()
     return lp
