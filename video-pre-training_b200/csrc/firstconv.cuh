@@ -1,10 +1,16 @@
 // Stack-0 first convolution, fully fused: u8 NHWC frame -> (x/255) conv3x3(3->C0)+bias -> ReLU -> max_pool(3,2,1)
-// -> bf16 NHWC + per-tile statistics partials.  K = 27 is far too small for the tensor pipe to matter; this layer is
-// bounded by its output write (C0*H*W/4 bf16 per frame) and by fp32 FMA issue.  fp32 FMAs keep the u8 input and the
-// fp32 weights exact (the first conv is the largest single contributor to bf16 error).
+// -> bf16 NHWC + per-tile statistics partials.
 //
-// One CTA = one 8x8 tile of POOLED outputs of one frame = 17x17 conv outputs = a 19x19x3 input patch.
+// K = 27 is too small for tcgen05 to matter (the layer is 0.75 % of the FLOPs and bounded by its epilogue / output
+// write), so the contraction runs on warp-level mma.sync m16n8k16: A = the im2col view of the u8 patch (u8 values
+// are exact in bf16; fragments are gathered straight from the patch in shared memory, no im2col copy), B = the fp32
+// weights split as bf16 hi + bf16 lo (K = 27 + 27 -> 64), fp32 accumulate: products are exact and the result is
+// fp32-accurate (the first conv is the largest single contributor to bf16 error otherwise).
+//
+// One CTA = one 8x8 tile of POOLED outputs of one frame = 17x17 conv outputs (19 m16 tiles) from a 19x19x3 patch.
+// ~99 KB of shared memory at C0 = 128 -> two CTAs per SM overlap one CTA's pooling with the other's MMAs.
 #pragma once
+#include "attention.cuh"  // ldsm_x4 / mma_bf16_16816
 #include "common.cuh"
 
 namespace vpt {
@@ -13,95 +19,159 @@ constexpr int kFcTile = 8;               // pooled outputs per tile edge
 constexpr int kFcConv = 2 * kFcTile + 1; // 17 conv rows/cols
 constexpr int kFcIn = kFcConv + 2;       // 19 input rows/cols
 constexpr int kFcThreads = 256;
+constexpr int kFcPos = kFcConv * kFcConv;        // 289 conv positions
+constexpr int kFcMTiles = (kFcPos + 15) / 16;    // 19
+constexpr int kFcBPitch = 72;                    // bf16 elements per weight row in smem (144 B: conflict-free ldmatrix)
+constexpr int kFcPatchElems = kFcIn * kFcIn * 3; // 1083
+constexpr int kFcPatchBytes = 2192;              // bf16 patch + one zero element, 16-byte multiple
 
-template <int CPT>  // channels per lane per pass; C0 = 32 * CPT * passes
-__global__ void __launch_bounds__(kFcThreads) firstconv_pool_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
-                                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                                    float2* __restrict__ stat_part, int H, int W, int C0) {
-    extern __shared__ uint8_t fc_smem[];
-    float* patch = reinterpret_cast<float*>(fc_smem);                                   // [19][19][3]
-    __nv_bfloat16* ctile = reinterpret_cast<__nv_bfloat16*>(fc_smem + 4352);            // [289][C0]
+__global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
+                                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                                       float2* __restrict__ stat_part, int H, int W, int C0, long long total_tiles) {
+    extern __shared__ __align__(16) uint8_t fc_smem[];
+    __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(fc_smem);                                  // [19][19][3]
+    __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(fc_smem + kFcPatchBytes);                     // [C0][72]
+    const int cpitch = C0 + 8;
+    __nv_bfloat16* ctile = Bs + (size_t)C0 * kFcBPitch;                                                // [289][C0+8]
     const int tiles_x = (W / 2) / kFcTile, tiles_y = (H / 2) / kFcTile;
     const int tiles = tiles_x * tiles_y;
-    const long long f = blockIdx.x / tiles;
-    const int tile = blockIdx.x % tiles;
+
+    // ---- hi/lo-split weights, staged once per (persistent) CTA
+    for (int i = threadIdx.x; i < C0 * 64; i += kFcThreads) {
+        const int n = i >> 6, k = i & 63;
+        float v = 0.f;
+        if (k < 27) {
+            v = __ldg(w + n * 27 + k);
+        } else if (k < 54) {
+            const float x = __ldg(w + n * 27 + k - 27);
+            v = x - __bfloat162float(__float2bfloat16_rn(x));
+        }
+        Bs[n * kFcBPitch + k] = __float2bfloat16_rn(v);
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+    // per-thread patch offsets of the k indices this lane feeds: k -> (ky, kx*3+c) -> ky*57 + q ; k in [27,54) repeats
+    int koff[4][4];
+    bool kval[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = 16 * s + 2 * tg + (e & 1) + ((e >> 1) << 3);
+            const int kk = k < 27 ? k : k - 27;
+            kval[s][e] = k < 54;
+            koff[s][e] = kval[s][e] ? (kk / 9) * (kFcIn * 3) + kk % 9 : 0;
+        }
+
+  for (long long tid = blockIdx.x; tid < total_tiles; tid += gridDim.x) {
+    const long long f = tid / tiles;
+    const int tile = (int)(tid % tiles);
     const int PY0 = (tile / tiles_x) * kFcTile, PX0 = (tile % tiles_x) * kFcTile;
     const int Yin0 = 2 * PY0 - 2, Xin0 = 2 * PX0 - 2;
     const uint8_t* fimg = img + f * (long long)H * W * 3;
-
-    for (int i = threadIdx.x; i < kFcIn * kFcIn * 3; i += kFcThreads) {
+    // ---- stage the input patch (u8 -> bf16, exact)
+    for (int i = threadIdx.x; i < kFcPatchElems; i += kFcThreads) {
         const int c = i % 3, ix = (i / 3) % kFcIn, iy = i / (3 * kFcIn);
         const int Y = Yin0 + iy, X = Xin0 + ix;
         float v = 0.f;
         if (Y >= 0 && Y < H && X >= 0 && X < W) v = (float)__ldg(fimg + ((long long)Y * W + X) * 3 + c);
-        patch[i] = v;
+        patch[i] = __float2bfloat16_rn(v);
     }
-    __syncthreads();
+    __syncthreads();  // patch (and, first time, weights) visible; previous tile's pooling finished reading ctile
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int passes = C0 / (32 * CPT);
-    for (int ps = 0; ps < passes; ++ps) {
-        const int c0 = (ps * 32 + lane) * CPT;
-        float wr[CPT][27];
-        float br[CPT];
+    for (int mt = warp; mt < kFcMTiles; mt += kFcThreads / 32) {
+        // A fragments (rows g and g+8 of this m-tile) for the 4 k-steps, gathered from the patch
+        int pos[2], pbase[2];
+        bool inimg[2];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            br[j] = __ldg(bias + c0 + j);
-#pragma unroll
-            for (int k = 0; k < 27; ++k) wr[j][k] = __ldg(w + (size_t)(c0 + j) * 27 + k);
-        }
-        for (int pos = warp; pos < kFcConv * kFcConv; pos += kFcThreads / 32) {
-            const int cy = pos / kFcConv, cx = pos % kFcConv;
+        for (int rr = 0; rr < 2; ++rr) {
+            const int p = min(mt * 16 + g + rr * 8, kFcPos - 1);
+            pos[rr] = mt * 16 + g + rr * 8;
+            const int cy = p / kFcConv, cx = p % kFcConv;
+            pbase[rr] = (cy * kFcIn + cx) * 3;
             const int Y = 2 * PY0 - 1 + cy, X = 2 * PX0 - 1 + cx;
-            float acc[CPT];
+            inimg[rr] = (Y >= 0 && Y < H && X >= 0 && X < W);
+        }
+        uint32_t af[4][4];
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) acc[j] = br[j];
-            if (Y >= 0 && Y < H && X >= 0 && X < W) {
+        for (int s = 0; s < 4; ++s) {
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const float* pr = patch + ((cy + ky) * kFcIn + cx) * 3;
+            for (int rr = 0; rr < 2; ++rr) {
 #pragma unroll
-                    for (int q = 0; q < 9; ++q) {
-                        const float xv = pr[q];
-#pragma unroll
-                        for (int j = 0; j < CPT; ++j) acc[j] = fmaf(xv, wr[j][ky * 9 + q], acc[j]);
-                    }
+                for (int hh = 0; hh < 2; ++hh) {  // hh = 0: k, k+1 ; hh = 1: k+8, k+9
+                    const uint16_t lo = kval[s][2 * hh] ? *reinterpret_cast<const uint16_t*>(patch + pbase[rr] + koff[s][2 * hh]) : (uint16_t)0;
+                    const uint16_t hi = kval[s][2 * hh + 1] ? *reinterpret_cast<const uint16_t*>(patch + pbase[rr] + koff[s][2 * hh + 1]) : (uint16_t)0;
+                    af[s][rr + 2 * hh] = (uint32_t)lo | ((uint32_t)hi << 16);
                 }
+            }
+        }
+        for (int nh = 0; nh < C0 / 64; ++nh) {  // 64 output channels at a time
+            float acc[8][4];
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) acc[j] = fmaxf(acc[j], 0.f);
-            } else {
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) acc[j] = 0.f;  // outside the image: neutral for the max (values are >= 0)
+            for (int nt = 0; nt < 8; ++nt) {
+                const float b0 = __ldg(bias + nh * 64 + nt * 8 + 2 * tg), b1 = __ldg(bias + nh * 64 + nt * 8 + 2 * tg + 1);
+                acc[nt][0] = b0; acc[nt][1] = b1; acc[nt][2] = b0; acc[nt][3] = b1;
             }
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) ctile[(size_t)pos * C0 + c0 + j] = __float2bfloat16_rn(acc[j]);
+            for (int s = 0; s < 4; ++s) {
+#pragma unroll
+                for (int np = 0; np < 4; ++np) {
+                    uint32_t b0, b1, b2, b3;
+                    const int nrow = nh * 64 + np * 16 + (lane & 7) + ((lane >> 4) << 3);
+                    const int kcol = s * 16 + (((lane >> 3) & 1) << 3);
+                    ldsm_x4(smem_u32(Bs + nrow * kFcBPitch + kcol), b0, b1, b2, b3);
+                    mma_bf16_16816(acc[2 * np], af[s][0], af[s][1], af[s][2], af[s][3], b0, b1);
+                    mma_bf16_16816(acc[2 * np + 1], af[s][0], af[s][1], af[s][2], af[s][3], b2, b3);
+                }
+            }
+            // ReLU; positions outside the image hold 0 (neutral for the max: every in-image value is >= 0)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (pos[rr] >= kFcPos) continue;
+                __nv_bfloat16* crow = ctile + (size_t)pos[rr] * cpitch + nh * 64 + 2 * tg;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const float v0 = inimg[rr] ? fmaxf(acc[nt][2 * rr], 0.f) : 0.f;
+                    const float v1 = inimg[rr] ? fmaxf(acc[nt][2 * rr + 1], 0.f) : 0.f;
+                    *reinterpret_cast<uint32_t*>(crow + nt * 8) = pack_bf16(v0, v1);
+                }
+            }
         }
     }
     __syncthreads();
 
-    // 3x3 / stride-2 max over the conv tile, two channels per item
-    const int C2 = C0 / 2;
+    // ---- 3x3 / stride-2 max over the conv tile, 8 channels (16 B) per item
+    const int C8 = C0 / 8;
     float s = 0.f, ss = 0.f;
     __nv_bfloat16* fout = out + f * (long long)(H / 2) * (W / 2) * C0;
-    for (int i = threadIdx.x; i < kFcTile * kFcTile * C2; i += kFcThreads) {
-        const int c2 = i % C2, px = (i / C2) % kFcTile, py = i / (C2 * kFcTile);
-        __nv_bfloat162 m = __floats2bfloat162_rn(0.f, 0.f);
+    for (int i = threadIdx.x; i < kFcTile * kFcTile * C8; i += kFcThreads) {
+        const int c8 = i % C8, px = (i / C8) % kFcTile, py = i / (C8 * kFcTile);
+        uint4 m = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const int pos = (2 * py + dy) * kFcConv + 2 * px + dx;
-                m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(ctile + (size_t)pos * C0 + 2 * c2));
+                const int p = (2 * py + dy) * kFcConv + 2 * px + dx;
+                const uint4 v = *reinterpret_cast<const uint4*>(ctile + (size_t)p * cpitch + 8 * c8);
+                m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
+                m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
             }
-        *reinterpret_cast<__nv_bfloat162*>(fout + ((long long)(PY0 + py) * (W / 2) + PX0 + px) * C0 + 2 * c2) = m;
-        const float a = __low2float(m), b = __high2float(m);
-        s += a + b;
-        ss = fmaf(a, a, fmaf(b, b, ss));
+        *reinterpret_cast<uint4*>(fout + ((long long)(PY0 + py) * (W / 2) + PX0 + px) * C0 + 8 * c8) = m;
+        const uint32_t w4[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
+            s += a + b;
+            ss = fmaf(a, a, fmaf(b, b, ss));
+        }
     }
     if (stat_part) {
-        const float2 r = block_sum2(s, ss);
+        const float2 r = block_sum2(s, ss);  // contains __syncthreads: also orders ctile / patch reuse
         if (threadIdx.x == 0) stat_part[f * tiles + tile] = r;
+    } else {
+        __syncthreads();
     }
+  }
 }
 
 }  // namespace vpt
@@ -116,20 +186,19 @@ extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const floa
     VPT_CHECK(C0 == 64 || C0 == 128 || C0 == 192 || C0 == 256, "vpt_firstconv_pool: C0=%d not in {64,128,192,256}", C0);
     const long long blocks = (long long)F * (H / 16) * (W / 16);
     VPT_CHECK(blocks < 2147483647LL, "vpt_firstconv_pool: too many tiles");
-    const size_t smem = 4352 + (size_t)kFcConv * kFcConv * C0 * 2;
-    cudaStream_t s = (cudaStream_t)stream;
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-    float2* sp = reinterpret_cast<float2*>(stat_part);
-#define VPT_FC(CPT)                                                                                                     \
-    do {                                                                                                                \
-        VPT_CUDA(cudaFuncSetAttribute(firstconv_pool_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        firstconv_pool_kernel<CPT><<<(unsigned)blocks, kFcThreads, smem, s>>>(img, w, bias, o, sp, H, W, C0);            \
-    } while (0)
-    if (C0 == 64) VPT_FC(2);
-    else if (C0 == 128) VPT_FC(4);
-    else if (C0 == 192) VPT_FC(3);
-    else VPT_FC(4);
-#undef VPT_FC
+    const size_t smem = kFcPatchBytes + (size_t)C0 * kFcBPitch * 2 + (size_t)kFcPos * (C0 + 8) * 2;
+    static size_t attr = 0;
+    if (smem > attr) {
+        VPT_CUDA(cudaFuncSetAttribute(firstconv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)num_sms() * per_sm;
+    if (grid > blocks) grid = blocks;
+    firstconv_pool_kernel<<<(unsigned)grid, kFcThreads, smem, (cudaStream_t)stream>>>(
+        img, w, bias, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<float2*>(stat_part), H, W, C0, blocks);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
