@@ -76,9 +76,12 @@ typedef struct vpt_gemm_args {
     int64_t seg_stride, seg_off;
     float* stat_part;         /* NULL or float2 partials of the stored values (see stat_mode) */
     int32_t stat_mode;        /* 1: [M][P] per row;  2: [ceil(M/32)][P] per 32 rows;  P = vpt_gemm_stat_parts(N) */
+    int32_t cluster;          /* CTAs per thread-block cluster sharing the B tile by TMA multicast: 0 = default, 1, 2, 4 */
 } vpt_gemm_args;
 
 int vpt_gemm_bf16(const vpt_gemm_args* args, void* stream);
+/* Cluster size used when vpt_gemm_args.cluster == 0 (tuning knob; 1, 2 or 4; initial value 2). */
+int vpt_set_default_cluster(int32_t cluster);
 /* Number of statistics partials per row (or per 32 rows) the GEMM emits for an N-column output. */
 int vpt_gemm_stat_parts(int32_t N);
 

@@ -29,7 +29,7 @@ def _row_stats(v, rows_per_group):
 
 
 def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, S2=None, relu=0, out_scale=1.0,
-         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0):
+         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0, cluster=0):
     Af = A.float()
     if conv is not None:
         H, W, Cin = conv

@@ -55,24 +55,25 @@ def _gemm_case(M, N, K, g, *, conv=None, fold=False, relu=0, residual=None, out_
     assert P == ops.gemm_stat_parts(N)
     srows = M if stats == 1 else (M + 31) // 32
 
-    def run(mod, dev):
+    def run(mod, dev, cluster=0):
         out = torch.zeros((rows_out, N), dtype=odt, device=dev)
         part = torch.zeros((srows, P, 2), dtype=F32, device=dev) if stats else None
         to = lambda t: None if t is None else t.to(dev)
         mod.gemm(to(A), to(Bw), out, M, N, K, conv=conv, mr=to(mr), rows_per_group=rpg, S1=to(S1), S2=to(S2), relu=relu, out_scale=out_scale,
-                 residual=to(res), seg=seg, stat_part=part, stat_mode=stats)
+                 residual=to(res), seg=seg, stat_part=part, stat_mode=stats, cluster=cluster)
         st = None
         if stats:
             npg = (rpg // 32 if stats == 2 else rpg) * P
             st = mod.stats_finalize(part, M // rpg, npg, rpg * N)
         return out, st
 
-    got, gst = run(ops, DEV)
-    nat.device_check()
     ref, rst = run(E, "cpu")
-    _close(f"gemm M={M} N={N} K={K} conv={conv} fold={fold}", got, ref)
-    if stats:
-        _close("gemm stats", gst, rst, rtol=2e-3, atol=2e-3, l2=1e-3)
+    for cluster in (1, 2, 4):  # CTAs per cluster sharing the B tile by TMA multicast
+        got, gst = run(ops, DEV, cluster)
+        nat.device_check()
+        _close(f"gemm M={M} N={N} K={K} conv={conv} fold={fold} cluster={cluster}", got, ref)
+        if stats:
+            _close(f"gemm stats cluster={cluster}", gst, rst, rtol=2e-3, atol=2e-3, l2=1e-3)
 
 
 def test_gemm_linear_plain():

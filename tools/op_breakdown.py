@@ -17,9 +17,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--width", default="2x")
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--timesteps", type=int, default=128)
+ap.add_argument("--cluster", type=int, default=0)
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
+if a.cluster:
+    ops.set_default_cluster(a.cluster)
 torch.manual_seed(0)
 pol = vpt_b200.MinecraftAgentPolicy(vpt_b200.minecraft_action_space(), vpt_b200.policy_kwargs(a.width), vpt_b200.PI_HEAD_KWARGS).to(dev)
 B, T = a.batch, a.timesteps

@@ -50,7 +50,7 @@ class GemmArgs(C.Structure):
         ("residual", C.c_void_p), ("residual_f32", C.c_int32), ("ld_res", C.c_int64),
         ("out", C.c_void_p), ("out_f32", C.c_int32), ("ld_out", C.c_int64),
         ("seg_len", C.c_int32), ("seg_stride", C.c_int64), ("seg_off", C.c_int64),
-        ("stat_part", C.c_void_p), ("stat_mode", C.c_int32),
+        ("stat_part", C.c_void_p), ("stat_mode", C.c_int32), ("cluster", C.c_int32),
     ]
 
 
@@ -64,6 +64,7 @@ SIGNATURES = {
     "vpt_num_sms": (_I, []),
     "vpt_gemm_bf16": (_I, [C.POINTER(GemmArgs), _P]),
     "vpt_gemm_stat_parts": (_I, [_I]),
+    "vpt_set_default_cluster": (_I, [_I]),
     "vpt_firstconv_pool": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vpt_firstconv_stat_parts": (_I, [_I, _I]),
     "vpt_maxpool3s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -24,6 +24,7 @@ constexpr uint32_t kStageBytesA = kBlockM * kBlockK * 2;
 struct GemmParams {
     int M, N, K;
     int block_n, num_m_tiles, num_n_tiles, k_iters, num_stages;
+    int cluster;  // CTAs per cluster; they work on consecutive M tiles of one N tile and share the B tile by TMA multicast
     int conv, H, W, cin_blocks, px_per_frame;
     // epilogue
     const float* mr;
@@ -75,7 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < p.num_stages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], (uint32_t)p.cluster);  // one MMA commit per CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
@@ -91,8 +92,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // peers must not multicast into / arrive on this CTA's barriers before they are initialised
+    if (p.cluster > 1) cluster_sync_all();
 
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int CS = p.cluster;
+    const int cta_rank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = blockIdx.x / CS, num_clusters = gridDim.x / CS;
+    const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+    // a "super tile" = CS consecutive M tiles of one N tile; CTA r of the cluster owns M tile group*CS + r
+    const int num_super = ((p.num_m_tiles + CS - 1) / CS) * p.num_n_tiles;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -100,8 +108,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+            const uint32_t slice_rows = (uint32_t)p.block_n / CS, slice_bytes = stage_bytes_b / CS;
+            for (int st = cluster_id; st < num_super && ok; st += num_clusters) {
+                const int m_tile = (st / p.num_n_tiles) * CS + cta_rank, n_tile = st % p.num_n_tiles;
                 const int m0 = m_tile * kBlockM, n0 = n_tile * p.block_n;
                 int f0 = 0, y0 = 0;
                 if (p.conv) {
@@ -120,7 +129,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         tma_load_2d(sa, &tmA, &full_bar[stage], it * kBlockK, m0);
                     }
-                    tma_load_2d(sb, &tmB, &full_bar[stage], it * kBlockK, n0);
+                    if (CS > 1)  // this CTA fetches 1/CS of the B tile and multicasts it to every CTA of the cluster
+                        tma_load_2d_mc(sb + cta_rank * slice_bytes, &tmB, &full_bar[stage], it * kBlockK, n0 + cta_rank * slice_rows, cmask);
+                    else
+                        tma_load_2d(sb, &tmB, &full_bar[stage], it * kBlockK, n0);
                     advance(stage, phase, p.num_stages);
                 }
             }
@@ -133,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             int local = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
+            for (int st = cluster_id; st < num_super && ok; st += num_clusters, ++local) {
                 const int as = local & 1;
                 const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
                 if (!(ok = mbar_wait(&tmem_empty_bar[as], aphase ^ 1u, 0x200u))) break;
@@ -149,7 +161,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                                   (uint32_t)((it | k) != 0));
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (CS > 1) umma_commit_mc(&empty_bar[stage], cmask);  // the slot is refilled by every CTA of the cluster
+                    else umma_commit(&empty_bar[stage]);
                     advance(stage, phase, p.num_stages);
                 }
                 if (ok) umma_commit(&tmem_full_bar[as]);
@@ -169,8 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool res_vec = ((p.ld_res & 7) == 0);
         int local = 0;
         bool ok = true;
-        for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
-            const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        for (int st = cluster_id; st < num_super && ok; st += num_clusters, ++local) {
+            const int m_tile = (st / p.num_n_tiles) * CS + cta_rank, n_tile = st % p.num_n_tiles;
             const int m0 = m_tile * kBlockM, n0 = n_tile * p.block_n;
             const int as = local & 1;
             const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
@@ -341,6 +354,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    // no CTA may exit while a peer can still multicast into its shared memory or arrive on its barriers
+    if (p.cluster > 1) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -394,6 +409,7 @@ static inline void choose_block_n(int N, int* block_n, int* n_tiles) {
     *n_tiles = (N + bn - 1) / bn;
 }
 
+static int g_default_cluster = 2;
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -405,6 +421,12 @@ static int num_sms() {
 }
 
 }  // namespace vpt
+
+extern "C" int vpt_set_default_cluster(int32_t cs) {
+    VPT_CHECK(cs == 1 || cs == 2 || cs == 4, "vpt_set_default_cluster: cluster size must be 1, 2 or 4");
+    vpt::g_default_cluster = cs;
+    return VPT_OK;
+}
 
 extern "C" int vpt_gemm_stat_parts(int32_t N) {
     int bn, nt;
@@ -459,10 +481,16 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
         p.k_iters = (a->K + kBlockK - 1) / kBlockK;
         p.px_per_frame = 1; p.W = 1; p.H = 1;
     }
+    // cluster size: CTAs of a cluster share the B tile (TMA multicast), which cuts L2->SM operand traffic per FLOP
+    int cs = a->cluster;
+    if (cs == 0) cs = g_default_cluster;
+    if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+    while (cs > 1 && (p.num_m_tiles < cs || p.block_n % (8 * cs) != 0)) cs >>= 1;
+    p.cluster = cs;
     {
         cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
         cuuint64_t strides[1] = {(cuuint64_t)a->K * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)p.block_n};
+        cuuint32_t box[2] = {64, (cuuint32_t)(p.block_n / cs)};
         int r = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
         if (r) return r;
     }
@@ -487,11 +515,34 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
         VPT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    int grid = num_sms();
-    if (grid <= 0) grid = 148;
-    if (grid > tiles) grid = tiles;
-    gemm_tc_kernel<<<grid, kGemmThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
-    VPT_LAUNCH_CHECK();
+    const int num_super = ((p.num_m_tiles + cs - 1) / cs) * p.num_n_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent grid: as many clusters as can be co-resident (cluster size 4 strands some SMs of the uneven GPCs)
+    static int max_clusters[5] = {0, 0, 0, 0, 0};
+    if (max_clusters[cs] == 0) {
+        int n = 0;
+        cfg.gridDim = dim3(num_sms() / cs * cs);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel, &cfg);
+        if (e != cudaSuccess || n <= 0) {
+            (void)cudaGetLastError();
+            n = num_sms() / cs;
+        }
+        max_clusters[cs] = n;
+    }
+    int clusters = max_clusters[cs];
+    if (clusters > num_super) clusters = num_super;
+    cfg.gridDim = dim3(clusters * cs);
+    VPT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, tmA, tmB, p));
     return VPT_OK;
 }

@@ -38,7 +38,7 @@ def _cuda(*ts):
 
 
 def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, S2=None, relu=0, out_scale=1.0,
-         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0):
+         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0, cluster=0):
     """out = epilogue(A @ Bw^T); see struct vpt_gemm_args."""
     _cuda(A, Bw, out)
     a = nat.GemmArgs()
@@ -53,7 +53,7 @@ def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, 
     a.ld_out = ld_out if ld_out is not None else out.stride(-2)
     if seg is not None:
         a.seg_len, a.seg_stride, a.seg_off = seg
-    a.stat_part, a.stat_mode = _p(stat_part), stat_mode
+    a.stat_part, a.stat_mode, a.cluster = _p(stat_part), stat_mode, cluster
     prof = GEMM_PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -64,6 +64,10 @@ def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, 
         prof.append((e0, e1, 2.0 * M * N * K, "conv" if conv is not None else "linear", (M, N, K)))
     _count()
     return out
+
+
+def set_default_cluster(cs):
+    nat.check(nat.lib().vpt_set_default_cluster(cs), "vpt_set_default_cluster")
 
 
 def gemm_stat_parts(N):
