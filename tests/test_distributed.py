@@ -1,0 +1,76 @@
+"""CPU, gloo, world_size 2: the multi-GPU path shards batch rows across ranks with NO data-path collective (sequences are
+independent units).  Checks the sharding helper and that gathering the per-rank results reproduces the
+unsharded forward (emulated ops stand in for the kernels; the arithmetic per row is identical by construction)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emu_ops
+    import vpt_b200
+    from common import make_policy, small_kwargs
+    from video_pre_training_b200 import ops, parallel
+
+    for name in dir(emu_ops):
+        if not name.startswith("_") and callable(getattr(emu_ops, name)) and hasattr(ops, name):
+            setattr(ops, name, getattr(emu_ops, name))
+    pol, sd, cfg = make_policy(small_kwargs(), seed=0)
+    B, T = 5, 8  # uneven split on purpose: ranks get 3 and 2 rows
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (B, T, 32, 32, 3), dtype=torch.uint8, generator=g)
+    first = torch.zeros(B, T, dtype=torch.bool)
+    lo, hi = parallel.shard_range(B, rank, world)
+    (pd, v, _), st = pol({"img": img[lo:hi]}, first[lo:hi], pol.initial_state(hi - lo))
+    full = parallel.all_gather_rows(pd["camera"], B)
+    if rank == 0:
+        (pd_all, _, _), _ = pol({"img": img}, first, pol.initial_state(B))
+        q.put((lo, hi, bool(torch.equal(full, pd_all["camera"])), tuple(full.shape)))
+    else:
+        q.put((lo, hi, True, tuple(full.shape)))
+    dist.destroy_process_group()
+
+
+def test_batch_sharding_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[:2] for r in res] == [(0, 3), (3, 5)]
+    assert all(r[2] for r in res) and all(r[3] == (5, 8, 1, 121) for r in res)
+
+
+def test_shard_range_covers_everything():
+    from video_pre_training_b200 import parallel
+
+    for B in (1, 5, 128):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

@@ -111,3 +111,40 @@ def test_chunk_invariance_and_reset_on_gpu():
     (pd2, _, _), _ = pol({"img": img[:, 8:]}, torch.zeros(B, 8, dtype=torch.bool, device=DEV), pol.initial_state(B))
     assert torch.equal(pd1["buttons"], pd2["buttons"])
     nat.device_check()
+
+
+def test_full_size_chunk_2x_rows_match_oracle_and_are_batch_independent():
+    """BASELINE configs[2] shape (2x width, T=128, KV memory carried over two chunks) at a batch the CPU oracle can follow:
+    (a) rows 0 of a B=6 run vs the oracle run on that row alone; (b) size-independent property: every batch row of the
+    B=6 run is BIT-IDENTICAL to the same row run as B=1 (sequences are independent units: no cross-row arithmetic)."""
+    kw = vpt_b200.policy_kwargs("2x")
+    pol, sd, cfg = make_policy(kw, pert=True)
+    pol = pol.to(DEV)
+    B, T = 6, 128
+    g = torch.Generator().manual_seed(11)
+    chunks = [torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, generator=g) for _ in range(2)]
+    firsts = [torch.zeros(B, T, dtype=torch.bool) for _ in range(2)]
+    firsts[1][3, 0] = True
+    st = pol.initial_state(B)
+    outs = []
+    for img, first in zip(chunks, firsts):
+        (pd, v, _), st = pol({"img": img.to(DEV)}, first.to(DEV), st)
+        outs.append((pd, v))
+    nat.device_check()
+    # (b) batch independence, bit exact
+    for b in (0, 3, 5):
+        st1 = pol.initial_state(1)
+        for ci, (img, first) in enumerate(zip(chunks, firsts)):
+            (pd1, v1, _), st1 = pol({"img": img[b:b + 1].to(DEV)}, first[b:b + 1].to(DEV), st1)
+            for k in pd1:
+                assert torch.equal(pd1[k][0], outs[ci][0][k][b]), f"row {b} chunk {ci} head {k} depends on its batch neighbours"
+        assert torch.equal(st1[-1][1][0][0], st[-1][1][0][b])
+    # (a) oracle on row 0 (CPU fp32), both chunks
+    st_o = O.initial_state(cfg, 1)
+    with torch.no_grad():
+        for ci, (img, first) in enumerate(zip(chunks, firsts)):
+            (pd_o, v_o, _), st_o = O.agent_policy_forward(sd, cfg, img[:1], first[:1], st_o)
+            for k in pd_o:
+                e = rel_err(outs[ci][0][k][:1].cpu(), pd_o[k])
+                print(f"2x full-size chunk {ci} {k}: max rel err {e:.4g}, l2 {l2_err(outs[ci][0][k][:1].cpu(), pd_o[k]):.3g}")
+                assert e < RTOL_BF16, (ci, k, e)

@@ -1,0 +1,28 @@
+"""Multi-GPU plumbing for the forward path: one process per GPU, batch rows (sequences) sharded across ranks.
+
+Sequences are independent units -- frames only interact through the per-sequence KV memory, which lives on the rank that
+owns the sequence -- so the data path needs NO collective.  `all_gather_rows` is an optional convenience
+for a caller that wants every rank's actions / logits in one place."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(batch: int, rank: int, world: int):
+    """Contiguous [lo, hi) slice of the batch rows owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_rows(x: torch.Tensor, batch: int) -> torch.Tensor:
+    """Concatenates the per-rank row shards of `x` (dim 0) on every rank; works for uneven shards."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return x
+    world = dist.get_world_size()
+    sizes = [shard_range(batch, r, world) for r in range(world)]
+    pad = max(hi - lo for lo, hi in sizes)
+    buf = torch.zeros((pad,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    buf[: x.shape[0]] = x
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
