@@ -86,18 +86,46 @@ int vpt_set_default_cluster(int32_t cluster);
 int vpt_gemm_stat_parts(int32_t N);
 
 /* ----------------------------------------------------------------------------------------------------------
+ * "ZP" activation layout used by the CNN: bf16 [F][H+1][W+1][C] whose last row (y = H) and last column (x = W) are zero.
+ * One shared zero row / column is all the padding a 3x3 pad-1 convolution needs when pixels are addressed linearly
+ * (row q = (f*(H+1) + y)*(W+1) + x): the neighbour (dy, dx) of q is row q + dy*(W+1) + dx.  Every producer below writes
+ * the zero row / column itself, so the invariant never depends on how the buffer was allocated.
+ *
+ * GroupNorm(1) -> Conv2d 3x3 pad 1 -> ReLU [+ residual] (lib/util.py:75-82 conv flavour, lib/impala_cnn.py:50-52) on ZP
+ * tensors.  Same fold as vpt_gemm_bf16(conv=1) (S1/S2 are [9][Cout] border-class tables), but the input rows are
+ * fetched ONCE per 64-channel block and reused by all nine taps from shared memory.
+ * -------------------------------------------------------------------------------------------------------- */
+typedef struct vpt_conv_zp_args {
+    const void* x;            /* bf16 ZP [F][H+1][W+1][Cin] */
+    const void* w;            /* bf16 [Cout][9*Cin], k = tap*Cin + c (tap = ky*3 + kx) */
+    int32_t F, H, W, Cin, Cout;
+    const float* mr;          /* [F][2] (mean, rstd) of x per frame, or NULL */
+    const float* S1;          /* [9][Cout] */
+    const float* S2;          /* [9][Cout] or NULL */
+    int32_t relu;             /* 0 none, 1 before the residual add, 2 after it */
+    const void* residual;     /* bf16 ZP [F][H+1][W+1][Cout] or NULL */
+    void* out;                /* bf16 ZP [F][H+1][W+1][Cout] */
+    float* stat_part;         /* NULL or float2 [F*(H+1)*(W+1)][vpt_conv_zp_stat_parts(Cout)] per-row partials */
+} vpt_conv_zp_args;
+
+int vpt_conv3x3_zp(const vpt_conv_zp_args* args, void* stream);
+int vpt_conv_zp_stat_parts(int32_t Cout);
+
+/* ----------------------------------------------------------------------------------------------------------
  * Stack-0 first convolution, fused:  u8 -> /255 -> Conv2d(3->C0, 3x3, pad 1) + bias -> ReLU -> max_pool2d(3, 2, 1)
  * (lib/policy.py:39-45, lib/util.py:79-81 with bias, lib/impala_cnn.py:115-117).
  *   img  u8   [F][H][W][3]      w  fp32 [C0][27] ordered (ky, kx, c), already divided by 255
- *   out  bf16 [F][H/2][W/2][C0] stat_part float2 [F][(H/16)*(W/16)]   (H, W multiples of 16; C0 in {64,128,192,256})
+ *   out  bf16 [F][H/2][W/2][C0] (zp=0) or ZP [F][H/2+1][W/2+1][C0] (zp=1)
+ *   stat_part float2 [F][(H/16)*(W/16)]   (H, W multiples of 16; C0 in {64,128,192,256})
  * -------------------------------------------------------------------------------------------------------- */
 int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part,
-                       int32_t F, int32_t H, int32_t W, int32_t C0, void* stream);
+                       int32_t F, int32_t H, int32_t W, int32_t C0, int32_t zp, void* stream);
 int vpt_firstconv_stat_parts(int32_t H, int32_t W);
 
 /* max_pool2d(kernel 3, stride 2, pad 1) on a non-negative NHWC bf16 tensor (lib/impala_cnn.py:117).
- *   in [F][H][W][C] -> out [F][H/2][W/2][C];  stat_part float2 [F][vpt_pool_stat_parts()] */
-int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
+ *   in [F][H][W][C] -> out [F][H/2][W/2][C]   (zp=1: both in the ZP layout, [F][H+1][W+1][C] -> [F][H/2+1][W/2+1][C])
+ *   stat_part float2 [F][vpt_pool_stat_parts()] */
+int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp, void* stream);
 int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C);
 
 /* out[m][c] = (in[m][c] - mean_g) * rstd_g * gamma[c] + beta[c],  g = m / rows_per_group   (bf16 in, bf16 out)
@@ -106,6 +134,10 @@ int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C);
  * stat_part float2 [G][vpt_norm_stat_parts(rows_per_group, C)]. */
 int vpt_affine_norm(const void* in, const float* mr, const float* gamma, const float* beta, void* out, float* out_f32,
                     float* stat_part, int64_t M, int32_t C, int32_t rows_per_group, void* stream);
+/* The same on ZP tensors [F][H+1][W+1][C], one group per frame: interior pixels are normalised, the zero row / column is
+ * rewritten as zero.  stat_part float2 [F][vpt_norm_stat_parts((H+1)*(W+1), C)]. */
+int vpt_affine_norm_zp(const void* in, const float* mr, const float* gamma, const float* beta, void* out, float* stat_part,
+                       int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
 int vpt_norm_stat_parts(int32_t rows_per_group, int32_t C);
 
 /* mr[g] = (mean, rsqrt(var + eps)) from n_per_group float2 partials per group; count = elements per group. */

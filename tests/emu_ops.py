@@ -95,19 +95,52 @@ def stats_finalize(part, G, n_per_group, count, eps=1e-5):
     return torch.stack([mean, 1.0 / torch.sqrt(var + eps)], 1).float()
 
 
-def firstconv_pool(img, w, bias, C0):
+def to_zp(x):
+    """[F,H,W,C] -> ZP [F,H+1,W+1,C] with a zero last row / column."""
+    return F.pad(x, (0, 0, 0, 1, 0, 1))
+
+
+def from_zp(x):
+    return x[:, :-1, :-1, :]
+
+
+def _frame_stats(x_interior):
+    return _row_stats(x_interior.reshape(x_interior.shape[0], -1), 1)
+
+
+def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True):
+    F_, Cin = x.shape[0], x.shape[3]
+    Cout = Wb.shape[0]
+    assert (x[:, -1] == 0).all() and (x[:, :, -1] == 0).all(), "ZP invariant violated on the conv input"
+    xi = from_zp(x).contiguous()
+    M = F_ * H * W
+    out = torch.zeros((M, Cout), dtype=BF16)
+    gemm(xi, Wb, out, M, Cout, 9 * Cin, conv=(H, W, Cin), mr=mr, rows_per_group=H * W, S1=S1, S2=S2, relu=relu,
+         residual=None if residual is None else from_zp(residual).contiguous())
+    o = out.reshape(F_, H, W, Cout)
+    return to_zp(o), (_frame_stats(o) if want_stats else None)
+
+
+def firstconv_pool(img, w, bias, C0, zp=True):
     F_, H, W, _ = img.shape
     x = img.float().permute(0, 3, 1, 2)
     wt = w.reshape(C0, 3, 3, 3).permute(0, 3, 1, 2)  # [C0][ky][kx][c] -> OIHW
     y = F.relu(F.conv2d(x, wt, bias, padding=1))
     y = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)
-    return y, _row_stats(y.reshape(F_, -1), 1)
+    return (to_zp(y) if zp else y), _frame_stats(y)
 
 
-def maxpool3s2(x):
-    F_ = x.shape[0]
-    y = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)
-    return y, _row_stats(y.reshape(F_, -1), 1)
+def maxpool3s2(x, zp=True):
+    xi = from_zp(x) if zp else x
+    y = F.max_pool2d(xi.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)
+    return (to_zp(y) if zp else y), _frame_stats(y)
+
+
+def affine_norm_zp(x, mr, gamma, beta):
+    xi = from_zp(x).float()
+    o = ((xi - mr[:, 0, None, None, None]) * mr[:, 1, None, None, None]) * gamma + beta
+    ob = o.to(BF16)
+    return to_zp(ob), _frame_stats(ob)
 
 
 def affine_norm(x, mr, gamma, beta, rows_per_group, want_stats=False, want_f32=False):

@@ -109,24 +109,67 @@ def test_gemm_conv3x3(H, W, Cin, Cout, F_):
     _gemm_case(F_ * H * W, Cout, 9 * Cin, g, conv=(H, W, Cin), fold=True, relu=1, residual=BF16, stats=mode)
 
 
+@pytest.mark.parametrize("H,W,Cin,Cout,F_", [(16, 16, 64, 64, 3), (8, 8, 128, 128, 5), (4, 4, 128, 128, 11), (32, 32, 128, 256, 2),
+                                             (64, 64, 128, 128, 3), (64, 64, 128, 256, 1), (16, 16, 256, 256, 3), (32, 32, 192, 384, 1),
+                                             (32, 32, 256, 256, 7)])
+def test_conv3x3_zp(H, W, Cin, Cout, F_):
+    """ZP-layout conv with the input span reused across the 9 taps (shifted UMMA descriptors) vs F.conv2d + fold."""
+    g = torch.Generator().manual_seed(13)
+    x = E.to_zp(_rand((F_, H, W, Cin), g))
+    Wb = _rand((Cout, 9 * Cin), g, (9 * Cin) ** -0.5)
+    mr = torch.stack([torch.randn(F_, generator=g) * 0.3, torch.rand(F_, generator=g) + 0.5], 1)
+    S1, S2 = torch.randn(9, Cout, generator=g), torch.randn(9, Cout, generator=g)
+    res = E.to_zp(_rand((F_, H, W, Cout), g))
+    for residual in (None, res):
+        got, gmr = ops.conv3x3_zp(x.to(DEV), Wb.to(DEV), H, W, mr=mr.to(DEV), S1=S1.to(DEV), S2=S2.to(DEV), relu=1,
+                                  residual=None if residual is None else residual.to(DEV))
+        nat.device_check()
+        ref, rmr = E.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, residual=residual)
+        gc = got.cpu()
+        assert (gc[:, -1] == 0).all() and (gc[:, :, -1] == 0).all(), "ZP zero row/column not maintained by the conv epilogue"
+        _close(f"conv3x3_zp {F_}x{H}x{W} {Cin}->{Cout} res={residual is not None}", got, ref)
+        _close("conv3x3_zp stats", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
+
+
+def test_zp_pool_norm():
+    g = torch.Generator().manual_seed(14)
+    x = E.to_zp(_rand((3, 16, 16, 128), g).relu())
+    got, gmr = ops.maxpool3s2(x.to(DEV), zp=True)
+    ref, rmr = E.maxpool3s2(x, zp=True)
+    assert torch.equal(got.cpu(), ref), "ZP maxpool must be bit exact (incl. zero row/column)"
+    _close("zp pool stats", gmr, rmr, rtol=1e-3, atol=1e-3, l2=1e-3)
+    gam, bet = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    got2, gmr2 = ops.affine_norm_zp(ref.to(DEV), rmr.to(DEV), gam.to(DEV), bet.to(DEV))
+    ref2, rmr2 = E.affine_norm_zp(ref, rmr, gam, bet)
+    nat.device_check()
+    g2 = got2.cpu()
+    assert (g2[:, -1] == 0).all() and (g2[:, :, -1] == 0).all()
+    _close("affine_norm_zp", got2, ref2, rtol=1e-2, atol=1e-2)
+    _close("affine_norm_zp stats", gmr2, rmr2, rtol=2e-3, atol=2e-3, l2=1e-3)
+
+
 def test_firstconv_pool():
     g = torch.Generator().manual_seed(4)
     for (F_, H, W, C0) in [(3, 32, 32, 64), (2, 128, 128, 128), (1, 64, 64, 192)]:
         img = torch.randint(0, 256, (F_, H, W, 3), dtype=torch.uint8, generator=g)
         w = torch.randn(C0, 27, generator=g) / 255.0 * 0.3
         b = torch.randn(C0, generator=g) * 0.1
-        got, gmr = ops.firstconv_pool(img.to(DEV), w.to(DEV), b.to(DEV), C0)
-        nat.device_check()
-        ref, rmr = E.firstconv_pool(img, w, b, C0)
-        _close(f"firstconv_pool {F_}x{H}x{W}x{C0}", got, ref, rtol=1e-2, atol=1e-3, l2=3e-3)
-        _close("firstconv stats", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
+        for zp in (True, False):
+            got, gmr = ops.firstconv_pool(img.to(DEV), w.to(DEV), b.to(DEV), C0, zp=zp)
+            nat.device_check()
+            ref, rmr = E.firstconv_pool(img, w, b, C0, zp=zp)
+            _close(f"firstconv_pool {F_}x{H}x{W}x{C0} zp={zp}", got, ref, rtol=1e-2, atol=1e-3, l2=3e-3)
+            _close("firstconv stats", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
+            if zp:
+                gc = got.cpu()
+                assert (gc[:, -1] == 0).all() and (gc[:, :, -1] == 0).all()
 
 
 def test_maxpool_and_affine_norm():
     g = torch.Generator().manual_seed(5)
     x = _rand((3, 16, 16, 128), g).relu()
-    got, gmr = ops.maxpool3s2(x.to(DEV))
-    ref, rmr = E.maxpool3s2(x)
+    got, gmr = ops.maxpool3s2(x.to(DEV), zp=False)
+    ref, rmr = E.maxpool3s2(x, zp=False)
     assert torch.equal(got.cpu(), ref), "maxpool must be bit exact"
     _close("pool stats", gmr, rmr, rtol=1e-3, atol=1e-3, l2=1e-3)
     gam, bet = torch.randn(128, generator=g), torch.randn(128, generator=g)

@@ -34,7 +34,7 @@ def _layer_report(r):
             ref = r["taps_o"][ko]
             tt = t.float().cpu()
             if tt.dim() == 4:
-                tt = tt.permute(0, 3, 1, 2)
+                tt = tt[:, :-1, :-1, :].permute(0, 3, 1, 2)  # ZP layout -> interior, NCHW
             rows.append(f"{k}: {l2_err(tt.reshape(ref.shape), ref):.3g}")
     return "; ".join(rows)
 

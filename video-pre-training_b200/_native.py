@@ -54,6 +54,16 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ConvZpArgs(C.Structure):
+    """struct vpt_conv_zp_args (include/vpt_b200.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p),
+        ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+        ("mr", C.c_void_p), ("S1", C.c_void_p), ("S2", C.c_void_p),
+        ("relu", C.c_int32), ("residual", C.c_void_p), ("out", C.c_void_p), ("stat_part", C.c_void_p),
+    ]
+
+
 _P, _I, _L, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); every symbol include/vpt_b200.h declares
@@ -65,11 +75,14 @@ SIGNATURES = {
     "vpt_gemm_bf16": (_I, [C.POINTER(GemmArgs), _P]),
     "vpt_gemm_stat_parts": (_I, [_I]),
     "vpt_set_default_cluster": (_I, [_I]),
-    "vpt_firstconv_pool": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "vpt_conv3x3_zp": (_I, [C.POINTER(ConvZpArgs), _P]),
+    "vpt_conv_zp_stat_parts": (_I, [_I]),
+    "vpt_firstconv_pool": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vpt_firstconv_stat_parts": (_I, [_I, _I]),
-    "vpt_maxpool3s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "vpt_maxpool3s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vpt_pool_stat_parts": (_I, [_I, _I, _I]),
     "vpt_affine_norm": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "vpt_affine_norm_zp": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vpt_norm_stat_parts": (_I, [_I, _I]),
     "vpt_stats_finalize": (_I, [_P, _P, _L, _I, _D, _F, _P]),
     "vpt_copy_rows": (_I, [_P, _I, _L, _L, _L, _P, _I, _L, _L, _L, _I, _I, _I, _P]),

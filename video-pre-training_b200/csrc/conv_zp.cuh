@@ -1,0 +1,392 @@
+// Implicit-GEMM 3x3 convolution on tcgen05 with the input tile REUSED across the 9 taps from shared memory.
+//
+// Measured on B200 (profiles/): a tcgen05 GEMM is bound by the bytes TMA can deliver INTO one SM
+// (~50-60 B/clk/SM), not by the tensor pipe, whenever a 128xN tile re-fetches A for every tap.  This kernel removes the
+// 9x A redundancy of implicit GEMM:
+//
+//   * activations live in the "ZP" layout [F][H+1][W+1][C] (bf16) whose row y=H and column x=W are zero: with one shared
+//     zero row / column every 3x3 neighbour of pixel q (a linear row index over the whole tensor) is the row q + dy*(W+1) + dx,
+//     so a tile of 128 (or 256) consecutive rows needs ONE contiguous span of  rows + 2*(W+2)  input rows per 64 channels;
+//   * the span is fetched once per 64-channel block by plain 2-D TMA (out-of-range rows are zero-filled) and all 9 taps are
+//     issued as UMMAs whose A descriptors start at span + ((dy+1)*(W+1) + dx+1)*128 B.  (Hardware fact, measured with
+//     tools/desc_experiment.py: for K-major SWIZZLE_128B operands the swizzle is a function of the absolute shared-memory
+//     address, so a descriptor start advanced by any multiple of 128 B reads the shifted rows correctly with base_offset 0.)
+//   * weights stream through their own pipeline, one [N][64] tile per (channel block, tap); with N <= 128 one CTA computes
+//     two 128-row sub-tiles per weight tile (M = 256), halving the weight bytes per FLOP as well.
+//
+//   warp 0: A-span TMA producer   warp 1: MMA issuer (+TMEM alloc)   warp 2: weight TMA producer   warps 3..10: epilogue
+// Epilogue = GroupNorm fold (border-class tables), ReLU, residual, bf16 store in ZP layout (border rows are written as
+// zeros, which maintains the layout invariant), per-row (sum, sumsq) partials for the next layer's statistics.
+#pragma once
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace vpt {
+
+constexpr int kCzThreads = 96 + 32 * kNumEpiWarps;  // 11 warps
+constexpr int kCzMaxBStages = 8;
+
+struct ConvZpParams {
+    long long Q;  // total rows = F * FS
+    int H, W, Wp, FS;
+    int N, block_n, num_n_tiles, cin, cin_blocks;
+    int mt;               // 128-row sub-tiles per CTA tile (1 or 2)
+    int a_box_rows, a_boxes, a_stage_bytes, b_stages;
+    long long num_m_tiles;
+    const float* mr;
+    const float* S1;
+    const float* S2;
+    int relu;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    float* stat_part;  // [Q][2 * num_n_tiles] float2 or null
+};
+
+__global__ void __launch_bounds__(kCzThreads, 1)
+conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvZpParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const uint32_t b_stage_bytes = (uint32_t)p.block_n * kBlockK * 2;
+    uint8_t* smem_a = smem;                                        // 2 A-span stages
+    uint8_t* smem_b = smem + 2 * (size_t)p.a_stage_bytes;          // b_stages weight tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_stage_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + 2;
+    uint64_t* b_full = bars + 4;
+    uint64_t* b_empty = bars + 4 + kCzMaxBStages;
+    uint64_t* tmem_full_bar = bars + 4 + 2 * kCzMaxBStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+        }
+        for (int i = 0; i < p.b_stages; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const long long num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tile_rows = p.mt * kBlockM;
+    const int halo = p.Wp + 1;  // rows before / after the tile that the taps reach
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= A-span producer =================
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+                const long long m_tile = tile / p.num_n_tiles;
+                const long long span0 = m_tile * tile_rows - halo;
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    if (!(ok = mbar_wait(&a_empty[stage], phase ^ 1u, 0x110u))) break;
+                    mbar_expect_tx(&a_full[stage], (uint32_t)p.a_stage_bytes);
+                    uint8_t* sa = smem_a + (size_t)stage * p.a_stage_bytes;
+                    for (int b = 0; b < p.a_boxes; ++b)
+                        tma_load_2d(sa + (size_t)b * p.a_box_rows * 128, &tmA, &a_full[stage], cb * kBlockK, (int)(span0 + (long long)b * p.a_box_rows));
+                    advance(stage, phase, 2);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ================= weight producer =================
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+                const int n0 = (int)(tile % p.num_n_tiles) * p.block_n;
+                for (int cb = 0; cb < p.cin_blocks && ok; ++cb) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!(ok = mbar_wait(&b_empty[stage], phase ^ 1u, 0x120u))) break;
+                        mbar_expect_tx(&b_full[stage], b_stage_bytes);
+                        tma_load_2d(smem_b + (size_t)stage * b_stage_bytes, &tmB, &b_full[stage], tap * p.cin + cb * kBlockK, n0);
+                        advance(stage, phase, p.b_stages);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n);
+            int astage = 0, bstage = 0;
+            uint32_t aphase_s = 0, bphase = 0;
+            int local = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
+                if (!(ok = mbar_wait(&tmem_empty_bar[as], accphase ^ 1u, 0x210u))) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStageCols);
+                for (int cb = 0; cb < p.cin_blocks && ok; ++cb) {
+                    if (!(ok = mbar_wait(&a_full[astage], aphase_s, 0x310u))) break;
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem_a + (size_t)astage * p.a_stage_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!(ok = mbar_wait(&b_full[bstage], bphase, 0x320u))) break;
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(smem_b + (size_t)bstage * b_stage_bytes);
+                        const int row_off = (tap / 3) * p.Wp + (tap % 3);  // (dy+1)*Wp + (dx+1)
+                        for (int j = 0; j < p.mt; ++j) {
+                            const uint32_t a_addr = a_base + (uint32_t)(row_off + j * kBlockM) * 128u;
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_bf16(d_tmem + (uint32_t)(j * p.block_n), umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
+                                          idesc, (uint32_t)((cb | tap | k) != 0));
+                        }
+                        umma_commit(&b_empty[bstage]);
+                        advance(bstage, bphase, p.b_stages);
+                    }
+                    if (!ok) break;
+                    umma_commit(&a_empty[astage]);
+                    advance(astage, aphase_s, 2);
+                }
+                if (ok) umma_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else {
+        // ================= epilogue (warps 3..10) =================
+        const int ew = warp - 3;
+        const int quarter = warp & 3;
+        const int grp = ew >> 2;  // mt == 1: column half; mt == 2: 128-row sub-tile
+        const int sub = (p.mt == 2) ? grp : 0;
+        const int nchunks = (p.block_n + 31) >> 5;
+        const int c_begin = (p.mt == 2 || grp == 0) ? 0 : (nchunks + 1) >> 1;
+        const int c_end = (p.mt == 2) ? nchunks : (grp == 0 ? (nchunks + 1) >> 1 : nchunks);
+        const int P = p.num_n_tiles * 2;
+        const bool tab_vec = ((p.N & 3) == 0);
+        int local = 0;
+        bool ok = true;
+        for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
+            const long long m_tile = tile / p.num_n_tiles;
+            const int n_tile = (int)(tile % p.num_n_tiles);
+            const int n0 = n_tile * p.block_n;
+            const int as = local & 1;
+            const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
+            const long long q = m_tile * tile_rows + sub * kBlockM + quarter * 32 + lane;
+            const bool row_ok = q < p.Q;
+            // decode the ZP row: frame, y, x
+            const long long f = q / p.FS;
+            const int r = (int)(q - f * p.FS);
+            const int y = r / p.Wp, x = r - y * p.Wp;
+            const bool interior = row_ok && (y < p.H) && (x < p.W);
+            float ga = 1.f, gb = 0.f;
+            if (p.mr != nullptr && interior) {
+                const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
+                ga = rstd;
+                gb = rstd * mean;
+            }
+            const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+            const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+            const int cls = interior ? cy * 3 + cx : 0;
+            const float* s1row = p.S1 ? p.S1 + (size_t)cls * p.N : nullptr;
+            const float* s2row = p.S2 ? p.S2 + (size_t)cls * p.N : nullptr;
+            float st_s = 0.f, st_ss = 0.f;
+
+            if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x410u))) break;
+            tc_fence_after();
+            for (int c = c_begin; c < c_end; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + sub * p.block_n + c * 32), acc);
+                tmem_ld_wait();
+                const int nb = n0 + c * 32;
+                const int lim = min(32, min(p.block_n - c * 32, p.N - nb));
+                if (!row_ok || lim <= 0) continue;
+                __nv_bfloat16* op = p.out + (size_t)q * p.N + nb;
+                const bool full = (lim == 32) && ((p.N & 7) == 0);
+                if (!interior) {  // zero row / column of the ZP layout
+                    if (full) {
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) reinterpret_cast<uint4*>(op)[qq] = make_uint4(0, 0, 0, 0);
+                    } else {
+                        for (int j = 0; j < lim; ++j) op[j] = __float2bfloat16_rn(0.f);
+                    }
+                    continue;
+                }
+                float v[32];
+                if (full && tab_vec) {
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        float4 a1 = s1row ? __ldg(reinterpret_cast<const float4*>(s1row + nb) + qq) : make_float4(0, 0, 0, 0);
+                        float4 a2 = s2row ? __ldg(reinterpret_cast<const float4*>(s2row + nb) + qq) : make_float4(0, 0, 0, 0);
+                        v[4 * qq + 0] = fmaf(ga, __uint_as_float(acc[4 * qq + 0]), fmaf(-gb, a1.x, a2.x));
+                        v[4 * qq + 1] = fmaf(ga, __uint_as_float(acc[4 * qq + 1]), fmaf(-gb, a1.y, a2.y));
+                        v[4 * qq + 2] = fmaf(ga, __uint_as_float(acc[4 * qq + 2]), fmaf(-gb, a1.z, a2.z));
+                        v[4 * qq + 3] = fmaf(ga, __uint_as_float(acc[4 * qq + 3]), fmaf(-gb, a1.w, a2.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float a1 = 0.f, a2 = 0.f;
+                        if (j < lim) {
+                            if (s1row) a1 = __ldg(s1row + nb + j);
+                            if (s2row) a2 = __ldg(s2row + nb + j);
+                        }
+                        v[j] = fmaf(ga, __uint_as_float(acc[j]), fmaf(-gb, a1, a2));
+                    }
+                }
+                if (p.relu == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (p.residual != nullptr) {
+                    const __nv_bfloat16* rp = p.residual + (size_t)q * p.N + nb;
+                    if (full) {
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            uint4 rr = __ldg(reinterpret_cast<const uint4*>(rp) + qq);
+                            v[8 * qq + 0] += bf16_lo(rr.x); v[8 * qq + 1] += bf16_hi(rr.x);
+                            v[8 * qq + 2] += bf16_lo(rr.y); v[8 * qq + 3] += bf16_hi(rr.y);
+                            v[8 * qq + 4] += bf16_lo(rr.z); v[8 * qq + 5] += bf16_hi(rr.z);
+                            v[8 * qq + 6] += bf16_lo(rr.w); v[8 * qq + 7] += bf16_hi(rr.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < lim) v[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                if (p.relu == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                if (p.stat_part) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+                        if (2 * j < lim) { st_s += lo; st_ss = fmaf(lo, lo, st_ss); }
+                        if (2 * j + 1 < lim) { st_s += hi; st_ss = fmaf(hi, hi, st_ss); }
+                    }
+                }
+                if (full) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq)
+                        reinterpret_cast<uint4*>(op)[qq] = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < lim) op[j] = __float2bfloat16_rn(v[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            if (p.stat_part && row_ok) {
+                float2* sp = reinterpret_cast<float2*>(p.stat_part) + (size_t)q * P + n_tile * 2;
+                if (p.mt == 2) {
+                    sp[0] = make_float2(st_s, st_ss);
+                    sp[1] = make_float2(0.f, 0.f);
+                } else {
+                    sp[grp] = make_float2(st_s, st_ss);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace vpt
+
+extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(a && a->x && a->w && a->out, "vpt_conv3x3_zp: null operand");
+    const int H = a->H, W = a->W, C = a->Cin, N = a->Cout;
+    VPT_CHECK(a->F > 0 && H >= 2 && W >= 2 && C > 0 && C % 64 == 0 && N > 0 && N % 16 == 0,
+              "vpt_conv3x3_zp: need F>0, H,W>=2, Cin %% 64 == 0, Cout %% 16 == 0 (F=%d H=%d W=%d Cin=%d Cout=%d)", a->F, H, W, C, N);
+    VPT_CHECK(W + 1 <= 255, "vpt_conv3x3_zp: W=%d too wide for one shared-memory span", W);
+    VPT_CHECK(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->w & 15) == 0 && ((uintptr_t)a->out & 15) == 0, "vpt_conv3x3_zp: pointers must be 16-byte aligned");
+    ConvZpParams p;
+    memset(&p, 0, sizeof(p));
+    p.H = H; p.W = W; p.Wp = W + 1; p.FS = (H + 1) * (W + 1);
+    p.Q = (long long)a->F * p.FS;
+    VPT_CHECK(p.Q < 2147483647LL, "vpt_conv3x3_zp: too many rows for 32-bit TMA coordinates");
+    p.N = N; p.cin = C; p.cin_blocks = C / 64;
+    choose_block_n(N, &p.block_n, &p.num_n_tiles);
+    p.mt = (p.block_n <= 128) ? 2 : 1;
+    const int tile_rows = p.mt * kBlockM;
+    p.num_m_tiles = (p.Q + tile_rows - 1) / tile_rows;
+    const int span = tile_rows + 2 * (p.Wp + 1);
+    p.a_boxes = (span + 255) / 256;
+    p.a_box_rows = ((span + p.a_boxes - 1) / p.a_boxes + 7) / 8 * 8;
+    VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
+    p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
+    const uint32_t b_stage_bytes = (uint32_t)p.block_n * kBlockK * 2;
+    const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - 512;
+    int bst = (int)(budget / b_stage_bytes);
+    if (bst > kCzMaxBStages) bst = kCzMaxBStages;
+    VPT_CHECK(bst >= 2, "vpt_conv3x3_zp: not enough shared memory for the weight pipeline (W=%d Cout=%d)", W, N);
+    p.b_stages = bst;
+    const size_t smem_bytes = 1024 + 2 * (size_t)p.a_stage_bytes + (size_t)bst * b_stage_bytes + (4 + 2 * kCzMaxBStages + 4) * 8 + 16;
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)p.Q};
+        cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.a_box_rows};
+        int r = make_tmap_bf16(&tmA, a->x, 2, dims, strides, box);
+        if (r) return r;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)9 * C, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)9 * C * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.block_n};
+        int r = make_tmap_bf16(&tmB, a->w, 2, dims, strides, box);
+        if (r) return r;
+    }
+    VPT_CHECK(!(a->mr && !a->S1), "vpt_conv3x3_zp: mr given without S1");
+    p.mr = a->mr; p.S1 = a->mr ? a->S1 : nullptr; p.S2 = a->S2; p.relu = a->relu;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+    p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.stat_part = a->stat_part;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const long long tiles = p.num_m_tiles * p.num_n_tiles;
+    long long grid = num_sms();
+    if (grid <= 0) grid = 148;
+    if (grid > tiles) grid = tiles;
+    conv3x3_zp_kernel<<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}
+
+extern "C" int vpt_conv_zp_stat_parts(int32_t Cout) {
+    int bn, nt;
+    vpt::choose_block_n(Cout, &bn, &nt);
+    return nt * 2;
+}

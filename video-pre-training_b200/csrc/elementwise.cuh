@@ -67,16 +67,21 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 }
 
 __global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
-                                                           float2* __restrict__ stat_part, int H, int W, int C8) {
+                                                           float2* __restrict__ stat_part, int H, int W, int C8, int zp) {
     const int Ho = H >> 1, Wo = W >> 1;
+    const int ipitch = W + zp, opitch = Wo + zp;  // ZP layout: one extra zero column (and row) per frame
     const long long f = blockIdx.y;
-    const int items = Ho * Wo * C8;
-    const uint4* fin = in + f * (long long)H * W * C8;
+    const int items = (Ho + zp) * opitch * C8;
+    const uint4* fin = in + f * (long long)(H + zp) * ipitch * C8;
     uint4* fout = out + f * (long long)items;
     float s = 0.f, ss = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
-        const int c = i % C8, px = (i / C8) % Wo, py = i / (C8 * Wo);
+        const int c = i % C8, px = (i / C8) % opitch, py = i / (C8 * opitch);
         uint4 m = make_uint4(0, 0, 0, 0);  // inputs are >= 0 (post-ReLU), so 0 == -inf padding
+        if (px >= Wo || py >= Ho) {  // zero column / row of the ZP output
+            fout[i] = m;
+            continue;
+        }
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
             const int y = 2 * py + dy;
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict
             for (int dx = -1; dx <= 1; ++dx) {
                 const int x = 2 * px + dx;
                 if (x < 0 || x >= W) continue;
-                const uint4 v = __ldg(fin + ((long long)y * W + x) * C8 + c);
+                const uint4 v = __ldg(fin + ((long long)y * ipitch + x) * C8 + c);
                 m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
                 m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
             }
@@ -136,6 +141,51 @@ __global__ void __launch_bounds__(256) affine_norm_kernel(const uint4* __restric
             of[0] = make_float4(x[0], x[1], x[2], x[3]);
             of[1] = make_float4(x[4], x[5], x[6], x[7]);
         }
+        const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
+            s += a + b;
+            ss = fmaf(a, a, fmaf(b, b, ss));
+        }
+    }
+    if (stat_part) {
+        const float2 r = block_sum2(s, ss);
+        if (threadIdx.x == 0) stat_part[g * gridDim.x + blockIdx.x] = r;
+    }
+}
+
+// ZP variant: one group per frame, [H+1][W+1][C8] items; the zero row / column is rewritten as zero
+__global__ void __launch_bounds__(256) affine_norm_zp_kernel(const uint4* __restrict__ in, const float2* __restrict__ mr,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               uint4* __restrict__ out, float2* __restrict__ stat_part, int H, int W, int C8) {
+    const long long g = blockIdx.y;
+    const float2 st = __ldg(mr + g);
+    const float mean = st.x, rstd = st.y;
+    const int Wp = W + 1;
+    const long long items = (long long)(H + 1) * Wp * C8;
+    const uint4* gin = in + g * items;
+    uint4* gout = out + g * items;
+    float s = 0.f, ss = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const int pix = (int)(i / C8);
+        const int y = pix / Wp, x = pix - y * Wp;
+        if (y >= H || x >= W) {
+            gout[i] = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        const uint4 v = __ldg(gin + i);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+        float xv[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y), bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = fmaf((xv[j] - mean) * rstd, ga[j], be[j]);
+        uint4 o;
+        o.x = pack_bf16(xv[0], xv[1]); o.y = pack_bf16(xv[2], xv[3]); o.z = pack_bf16(xv[4], xv[5]); o.w = pack_bf16(xv[6], xv[7]);
+        gout[i] = o;
         const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -224,14 +274,14 @@ extern "C" int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C) {
     return vpt_blocks_for((long long)(H / 2) * (W / 2) * (C / 8), 2048, 64);
 }
 
-extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, void* stream) {
+extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp, void* stream) {
     using namespace vpt;
     VPT_CHECK(in && out && F > 0, "vpt_maxpool3s2: null argument");
     VPT_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vpt_maxpool3s2: need even H, W and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
     VPT_CHECK(F <= 65535, "vpt_maxpool3s2: at most 65535 frames per call (got %d)", F);
     dim3 grid(vpt_pool_stat_parts(H, W, C), F);
     maxpool3s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
-                                                            reinterpret_cast<float2*>(stat_part), H, W, C / 8);
+                                                            reinterpret_cast<float2*>(stat_part), H, W, C / 8, zp ? 1 : 0);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
@@ -256,6 +306,24 @@ extern "C" int vpt_affine_norm(const void* in, const float* mr, const float* gam
             reinterpret_cast<const uint4*>(in) + g0 * items, reinterpret_cast<const float2*>(mr) + g0, gamma, beta,
             reinterpret_cast<uint4*>(out) + g0 * items, out_f32 ? out_f32 + g0 * items * 8 : nullptr,
             stat_part ? reinterpret_cast<float2*>(stat_part) + g0 * bpg : nullptr, items, C / 8);
+        VPT_LAUNCH_CHECK();
+    }
+    return VPT_OK;
+}
+
+extern "C" int vpt_affine_norm_zp(const void* in, const float* mr, const float* gamma, const float* beta, void* out, float* stat_part,
+                                  int32_t F, int32_t H, int32_t W, int32_t C, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(in && mr && gamma && beta && out && F > 0, "vpt_affine_norm_zp: null argument");
+    VPT_CHECK(C % 8 == 0 && H > 0 && W > 0, "vpt_affine_norm_zp: need C %% 8 == 0");
+    const long long items = (long long)(H + 1) * (W + 1) * (C / 8);
+    const int bpg = vpt_norm_stat_parts((H + 1) * (W + 1), C);
+    for (long long g0 = 0; g0 < F; g0 += 65535) {
+        const long long gn = (F - g0 < 65535) ? (F - g0) : 65535;
+        dim3 grid(bpg, (unsigned)gn);
+        affine_norm_zp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(in) + g0 * items, reinterpret_cast<const float2*>(mr) + g0, gamma, beta,
+            reinterpret_cast<uint4*>(out) + g0 * items, stat_part ? reinterpret_cast<float2*>(stat_part) + g0 * bpg : nullptr, H, W, C / 8);
         VPT_LAUNCH_CHECK();
     }
     return VPT_OK;

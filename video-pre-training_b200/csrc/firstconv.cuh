@@ -27,7 +27,7 @@ constexpr int kFcPatchBytes = 2192;              // bf16 patch + one zero elemen
 
 __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
                                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                                       float2* __restrict__ stat_part, int H, int W, int C0, long long total_tiles) {
+                                                                       float2* __restrict__ stat_part, int H, int W, int C0, long long total_tiles, int zp) {
     extern __shared__ __align__(16) uint8_t fc_smem[];
     __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(fc_smem);                                  // [19][19][3]
     __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(fc_smem + kFcPatchBytes);                     // [C0][72]
@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uin
     // ---- 3x3 / stride-2 max over the conv tile, 8 channels (16 B) per item
     const int C8 = C0 / 8;
     float s = 0.f, ss = 0.f;
-    __nv_bfloat16* fout = out + f * (long long)(H / 2) * (W / 2) * C0;
+    const int Ho = H / 2, Wo = W / 2, opitch = Wo + zp;  // ZP layout: one extra zero column / row
+    __nv_bfloat16* fout = out + f * (long long)(Ho + zp) * opitch * C0;
     for (int i = threadIdx.x; i < kFcTile * kFcTile * C8; i += kFcThreads) {
         const int c8 = i % C8, px = (i / C8) % kFcTile, py = i / (C8 * kFcTile);
         uint4 m = make_uint4(0, 0, 0, 0);
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uin
                 m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
                 m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
             }
-        *reinterpret_cast<uint4*>(fout + ((long long)(PY0 + py) * (W / 2) + PX0 + px) * C0 + 8 * c8) = m;
+        *reinterpret_cast<uint4*>(fout + ((long long)(PY0 + py) * opitch + PX0 + px) * C0 + 8 * c8) = m;
         const uint32_t w4[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -164,6 +165,15 @@ __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uin
             s += a + b;
             ss = fmaf(a, a, fmaf(b, b, ss));
         }
+    }
+    if (zp) {  // edge tiles write the zero column x = Wo and the zero row y = Ho (plus the corner)
+        const bool right = (PX0 + kFcTile == Wo), bottom = (PY0 + kFcTile == Ho);
+        if (right)
+            for (int i = threadIdx.x; i < kFcTile * C8; i += kFcThreads)
+                *reinterpret_cast<uint4*>(fout + ((long long)(PY0 + i / C8) * opitch + Wo) * C0 + 8 * (i % C8)) = make_uint4(0, 0, 0, 0);
+        if (bottom)
+            for (int i = threadIdx.x; i < (kFcTile + (right ? 1 : 0)) * C8; i += kFcThreads)
+                *reinterpret_cast<uint4*>(fout + ((long long)Ho * opitch + PX0 + i / C8) * C0 + 8 * (i % C8)) = make_uint4(0, 0, 0, 0);
     }
     if (stat_part) {
         const float2 r = block_sum2(s, ss);  // contains __syncthreads: also orders ctile / patch reuse
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uin
 extern "C" int vpt_firstconv_stat_parts(int32_t H, int32_t W) { return (H / 16) * (W / 16); }
 
 extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part, int32_t F,
-                                  int32_t H, int32_t W, int32_t C0, void* stream) {
+                                  int32_t H, int32_t W, int32_t C0, int32_t zp, void* stream) {
     using namespace vpt;
     VPT_CHECK(img && w && bias && out && F > 0, "vpt_firstconv_pool: null argument");
     VPT_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "vpt_firstconv_pool: H, W must be multiples of 16 (H=%d W=%d)", H, W);
@@ -198,7 +208,7 @@ extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const floa
     long long grid = (long long)num_sms() * per_sm;
     if (grid > blocks) grid = blocks;
     firstconv_pool_kernel<<<(unsigned)grid, kFcThreads, smem, (cudaStream_t)stream>>>(
-        img, w, bias, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<float2*>(stat_part), H, W, C0, blocks);
+        img, w, bias, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<float2*>(stat_part), H, W, C0, blocks, zp ? 1 : 0);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

@@ -24,6 +24,7 @@ constexpr uint32_t kStageBytesA = kBlockM * kBlockK * 2;
 struct GemmParams {
     int M, N, K;
     int block_n, num_m_tiles, num_n_tiles, k_iters, num_stages;
+    int dbg_shift, dbg_bo;  // descriptor experiment: A rows loaded `dbg_shift` rows early, MMA start advanced to compensate
     int cluster;  // CTAs per cluster; they work on consecutive M tiles of one N tile and share the B tile by TMA multicast
     int conv, H, W, cin_blocks, px_per_frame;
     // epilogue
@@ -127,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
                         tma_load_4d(sa, &tmA, &full_bar[stage], cb * kBlockK, dx, y0 + dy, f0);
                     } else {
-                        tma_load_2d(sa, &tmA, &full_bar[stage], it * kBlockK, m0);
+                        tma_load_2d(sa, &tmA, &full_bar[stage], it * kBlockK, m0 - p.dbg_shift);
                     }
                     if (CS > 1)  // this CTA fetches 1/CS of the B tile and multicasts it to every CTA of the cluster
                         tma_load_2d_mc(sb + cta_rank * slice_bytes, &tmB, &full_bar[stage], it * kBlockK, n0 + cta_rank * slice_rows, cmask);
@@ -154,11 +155,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int it = 0; it < p.k_iters; ++it) {
                     if (!(ok = mbar_wait(&full_bar[stage], phase, 0x300u))) break;
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kStageBytesA);
+                    const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kStageBytesA) + (uint32_t)p.dbg_shift * 128u;
+                    const uint64_t a_bo = p.dbg_bo ? ((uint64_t)((a_addr >> 7) & 7u) << 49) : 0ull;
                     const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * stage_bytes_b);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32) | a_bo, umma_desc_sw128(b_addr + k * 32), idesc,
                                   (uint32_t)((it | k) != 0));
                     }
                     if (CS > 1) umma_commit_mc(&empty_bar[stage], cmask);  // the slot is refilled by every CTA of the cluster
@@ -409,7 +411,8 @@ static inline void choose_block_n(int N, int* block_n, int* n_tiles) {
     *n_tiles = (N + bn - 1) / bn;
 }
 
-static int g_default_cluster = 2;
+static int g_default_cluster = 1;
+static int g_dbg_shift = 0, g_dbg_bo = 0;
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -425,6 +428,12 @@ static int num_sms() {
 extern "C" int vpt_set_default_cluster(int32_t cs) {
     VPT_CHECK(cs == 1 || cs == 2 || cs == 4, "vpt_set_default_cluster: cluster size must be 1, 2 or 4");
     vpt::g_default_cluster = cs;
+    return VPT_OK;
+}
+
+extern "C" int vpt_debug_set(int32_t shift, int32_t bo) {
+    vpt::g_dbg_shift = shift;
+    vpt::g_dbg_bo = bo;
     return VPT_OK;
 }
 
@@ -487,6 +496,7 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     if (cs != 1 && cs != 2 && cs != 4) cs = 1;
     while (cs > 1 && (p.num_m_tiles < cs || p.block_n % (8 * cs) != 0)) cs >>= 1;
     p.cluster = cs;
+    p.dbg_shift = g_dbg_shift; p.dbg_bo = g_dbg_bo;
     {
         cuuint64_t dims[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
         cuuint64_t strides[1] = {(cuuint64_t)a->K * 2};

@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace vpt
 
 #include "gemm_tc.cuh"
+#include "conv_zp.cuh"
 #include "elementwise.cuh"
 #include "firstconv.cuh"
 #include "attention.cuh"

@@ -81,26 +81,53 @@ def stats_finalize(part, G, n_per_group, count, eps=1e-5):
     return mr
 
 
-def firstconv_pool(img, w, bias, C0):
-    """img u8 [F,H,W,3] -> (bf16 [F,H/2,W/2,C0], per-frame (mean, rstd))."""
+def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True):
+    """GroupNorm(1)->conv3x3->ReLU[+residual] on a ZP tensor x bf16 [F,H+1,W+1,Cin]; returns (ZP out, per-frame (mean, rstd))."""
+    _cuda(x, Wb)
+    F_, Cin = x.shape[0], x.shape[3]
+    Cout = Wb.shape[0]
+    assert tuple(x.shape[1:3]) == (H + 1, W + 1) and Wb.shape[1] == 9 * Cin
+    out = torch.empty((F_, H + 1, W + 1, Cout), dtype=BF16, device=x.device)
+    P = nat.lib().vpt_conv_zp_stat_parts(Cout)
+    part = torch.empty((F_ * (H + 1) * (W + 1), P, 2), dtype=F32, device=x.device) if want_stats else None
+    a = nat.ConvZpArgs()
+    a.x, a.w, a.F, a.H, a.W, a.Cin, a.Cout = _p(x), _p(Wb), F_, H, W, Cin, Cout
+    a.mr, a.S1, a.S2, a.relu, a.residual, a.out, a.stat_part = _p(mr), _p(S1), _p(S2), relu, _p(residual), _p(out), _p(part)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    nat.check(nat.lib().vpt_conv3x3_zp(C.byref(a), _stream()), "vpt_conv3x3_zp")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * F_ * H * W * Cout * 9 * Cin, "conv", (F_ * H * W, Cout, 9 * Cin)))  # algorithmic FLOPs (no halo rows)
+    _count()
+    mr_out = stats_finalize(part, F_, (H + 1) * (W + 1) * P, H * W * Cout) if want_stats else None
+    return out, mr_out
+
+
+def firstconv_pool(img, w, bias, C0, zp=True):
+    """img u8 [F,H,W,3] -> (bf16 [F,H/2(+1),W/2(+1),C0] (ZP layout when zp), per-frame (mean, rstd))."""
     _cuda(img, w, bias)
     F_, H, W, _ = img.shape
-    out = torch.empty((F_, H // 2, W // 2, C0), dtype=BF16, device=img.device)
+    z = int(zp)
+    out = torch.empty((F_, H // 2 + z, W // 2 + z, C0), dtype=BF16, device=img.device)
     P = nat.lib().vpt_firstconv_stat_parts(H, W)
     part = torch.empty((F_, P, 2), dtype=F32, device=img.device)
-    nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, _stream()), "vpt_firstconv_pool")
+    nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, z, _stream()), "vpt_firstconv_pool")
     _count()
     return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * C0)
 
 
-def maxpool3s2(x):
-    """bf16 [F,H,W,C] (>= 0) -> (bf16 [F,H/2,W/2,C], per-frame (mean, rstd))."""
+def maxpool3s2(x, zp=True):
+    """bf16 [F,H,W,C] (>= 0) -> (bf16 [F,H/2,W/2,C], per-frame (mean, rstd)); with zp both tensors are ZP ([F,H+1,W+1,C])."""
     _cuda(x)
-    F_, H, W, Cc = x.shape
-    out = torch.empty((F_, H // 2, W // 2, Cc), dtype=BF16, device=x.device)
+    z = int(zp)
+    F_, H, W, Cc = x.shape[0], x.shape[1] - z, x.shape[2] - z, x.shape[3]
+    out = torch.empty((F_, H // 2 + z, W // 2 + z, Cc), dtype=BF16, device=x.device)
     P = nat.lib().vpt_pool_stat_parts(H, W, Cc)
     part = torch.empty((F_, P, 2), dtype=F32, device=x.device)
-    nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), F_, H, W, Cc, _stream()), "vpt_maxpool3s2")
+    nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), F_, H, W, Cc, z, _stream()), "vpt_maxpool3s2")
     _count()
     return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * Cc)
 
@@ -122,6 +149,18 @@ def affine_norm(x, mr, gamma, beta, rows_per_group, want_stats=False, want_f32=F
     _count()
     mr_out = stats_finalize(part, G, P, rows_per_group * Cc) if want_stats else None
     return out, out32, mr_out
+
+
+def affine_norm_zp(x, mr, gamma, beta):
+    """GroupNorm(1) application on a ZP tensor [F,H+1,W+1,C] (one group per frame); returns (ZP out, (mean, rstd) of out)."""
+    _cuda(x, mr, gamma, beta)
+    F_, H, W, Cc = x.shape[0], x.shape[1] - 1, x.shape[2] - 1, x.shape[3]
+    out = torch.empty_like(x)
+    P = nat.lib().vpt_norm_stat_parts((H + 1) * (W + 1), Cc)
+    part = torch.empty((F_, P, 2), dtype=F32, device=x.device)
+    nat.check(nat.lib().vpt_affine_norm_zp(_p(x), _p(mr), _p(gamma), _p(beta), _p(out), _p(part), F_, H, W, Cc, _stream()), "vpt_affine_norm_zp")
+    _count()
+    return out, stats_finalize(part, F_, P, H * W * Cc)
 
 
 def copy_rows(src, src_off, dst, dst_off, rows):

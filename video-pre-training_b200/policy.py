@@ -220,8 +220,12 @@ class _Prepared:
             self.stacks.append(st)
         C2 = cfg.chans[-1]
         Hf, Wf = cfg.final_hw
-        # dense: reference flatten order is c*H*W + h*W + w (lib/impala_cnn.py:192-193); ours is NHWC
-        perm = lambda v: v.reshape(*v.shape[:-1], C2, Hf, Wf).movedim(-3, -1).reshape(*v.shape[:-1], -1)
+        # dense: reference flatten order is c*H*W + h*W + w (lib/impala_cnn.py:192-193); ours is the ZP layout
+        # [Hf+1][Wf+1][C2] -> permute to (h, w, c) and insert zero columns where the layout holds its zero row / column
+        def perm(v):
+            v = v.reshape(*v.shape[:-1], C2, Hf, Wf).movedim(-3, -1)          # (..., Hf, Wf, C2)
+            v = torch.nn.functional.pad(v, (0, 0, 0, 1, 0, 1))                # (..., Hf+1, Wf+1, C2)
+            return v.reshape(*v.shape[:-3], -1)
         self.dense = _fold_linear(perm(g(f"{p}.dense.layer.weight")), perm(g(f"{p}.dense.norm.weight")), perm(g(f"{p}.dense.norm.bias")))
         self.linear = _fold_linear(g("img_process.linear.layer.weight"), g("img_process.linear.norm.weight"), g("img_process.linear.norm.bias"))
         self.layers = []
@@ -289,48 +293,35 @@ class MinecraftPolicy(nn.Module):
             self.debug_taps[name] = t
 
     # -- CNN -----------------------------------------------------------------------------------------------
-    def _conv(self, x, mr, fold, H, W, Cin, Cout, relu=1, residual=None, want_stats=True):
-        """One GroupNorm(1)->conv3x3->ReLU[+residual] layer on bf16 NHWC `x` [F,H,W,Cin] whose per-frame stats are `mr`."""
-        Wb, S1, S2 = fold
-        F_ = x.shape[0]
-        M = F_ * H * W
-        out = torch.empty((F_, H, W, Cout), dtype=BF16, device=x.device)
-        part, mode, P, npg = None, 0, ops.gemm_stat_parts(Cout), 0
-        if want_stats:
-            mode = 2 if (H * W) % 32 == 0 else 1
-            rows = (M + 31) // 32 if mode == 2 else M
-            part = torch.empty((rows, P, 2), dtype=F32, device=x.device)
-            npg = (H * W // 32 if mode == 2 else H * W) * P
-        ops.gemm(x, Wb, out, M, Cout, 9 * Cin, conv=(H, W, Cin), mr=mr, rows_per_group=H * W, S1=S1, S2=S2, relu=relu,
-                 residual=residual, ld_out=Cout, stat_part=part, stat_mode=mode)
-        mr_out = ops.stats_finalize(part, F_, npg, H * W * Cout) if want_stats else None
-        return out, mr_out
-
+    # Activations are kept in the "ZP" layout [F][H+1][W+1][C] (zero last row / column; include/vpt_b200.h): it lets the
+    # conv kernel address every 3x3 neighbour linearly and reuse one shared-memory input span for all nine taps.
     def _cnn_chunk(self, img, prep: _Prepared, pfx="img_process.cnn"):
-        """lib/impala_cnn.py:187-195 for a chunk of frames; returns (x [F, Hf, Wf, C2] bf16, per-frame stats)."""
+        """lib/impala_cnn.py:187-195 for a chunk of frames; returns (x ZP [F, Hf+1, Wf+1, C2] bf16, per-frame stats)."""
         cfg = self.cfg
         H, W = cfg.img_shape[0], cfg.img_shape[1]
-        x, mr, cin = None, None, 3
+        x, mr = None, None
         for i, c in enumerate(cfg.chans):
             st = prep.stacks[i]
             if i == 0 and "fc_w" in st:
-                y1, mr1 = ops.firstconv_pool(img, st["fc_w"], st["fc_b"], c)
+                y1, mr1 = ops.firstconv_pool(img, st["fc_w"], st["fc_b"], c, zp=True)
             else:
-                full, _ = self._conv(x, mr, st["first"], H, W, cin, c, want_stats=False)
-                y1, mr1 = ops.maxpool3s2(full)
+                Wb, S1, S2 = st["first"]
+                full, _ = ops.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, want_stats=False)
+                y1, mr1 = ops.maxpool3s2(full, zp=True)
                 del full
             H, W = H // 2, W // 2
             self._tap(f"{pfx}.stacks.{i}.pool", y1)
             # post-pool GroupNorm `n` (lib/impala_cnn.py:119): materialised because it is the residual stream
-            x, _, mr = ops.affine_norm(y1, mr1, st["n_g"], st["n_b"], rows_per_group=H * W, want_stats=True)
+            x, mr = ops.affine_norm_zp(y1, mr1, st["n_g"], st["n_b"])
             del y1
             self._tap(f"{pfx}.stacks.{i}.n", x)
             for j in range(2):
-                hmid, mrh = self._conv(x, mr, st["convs"][2 * j], H, W, c, c)
+                Wb, S1, S2 = st["convs"][2 * j]
+                hmid, mrh = ops.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1)
                 self._tap(f"{pfx}.stacks.{i}.blocks.{j}.conv0", hmid)
-                x, mr = self._conv(hmid, mrh, st["convs"][2 * j + 1], H, W, c, c, residual=x)
+                Wb, S1, S2 = st["convs"][2 * j + 1]
+                x, mr = ops.conv3x3_zp(hmid, Wb, H, W, mr=mrh, S1=S1, S2=S2, relu=1, residual=x)
                 self._tap(f"{pfx}.stacks.{i}.blocks.{j}", x)
-            cin = c
         return x, mr
 
     # -- transformer -----------------------------------------------------------------------------------------
@@ -411,7 +402,8 @@ class MinecraftPolicy(nn.Module):
         for f0 in range(0, N, self.cnn_chunk_frames):
             F_ = min(self.cnn_chunk_frames, N - f0)
             x, mr = self._cnn_chunk(frames[f0:f0 + F_], prep)
-            ops.gemm(x.view(F_, Hf * Wf * C2), Wd, xd[f0:f0 + F_], F_, cfg.cnn_outsize, Hf * Wf * C2, mr=mr, rows_per_group=1,
+            Kd = (Hf + 1) * (Wf + 1) * C2  # ZP rows flattened; the zero row / column meets zero weight columns
+            ops.gemm(x.view(F_, Kd), Wd, xd[f0:f0 + F_], F_, cfg.cnn_outsize, Kd, mr=mr, rows_per_group=1,
                      S1=S1d, S2=S2d, relu=1, stat_part=part_d[f0:f0 + F_], stat_mode=1)
             del x, mr
         mr_d = ops.stats_finalize(part_d, N, Pd, cfg.cnn_outsize)
