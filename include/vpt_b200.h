@@ -82,6 +82,9 @@ typedef struct vpt_gemm_args {
 int vpt_gemm_bf16(const vpt_gemm_args* args, void* stream);
 /* Cluster size used when vpt_gemm_args.cluster == 0 (tuning knob; 1, 2 or 4; initial value 2). */
 int vpt_set_default_cluster(int32_t cluster);
+/* Hardware experiment hook used by tools/desc_experiment.py (A rows loaded `shift` rows early, UMMA descriptor start
+ * advanced to compensate, base_offset field on/off).  Not for production use. */
+int vpt_debug_set(int32_t shift, int32_t base_offset_mode);
 /* Number of statistics partials per row (or per 32 rows) the GEMM emits for an N-column output. */
 int vpt_gemm_stat_parts(int32_t N);
 
@@ -109,6 +112,9 @@ typedef struct vpt_conv_zp_args {
 } vpt_conv_zp_args;
 
 int vpt_conv3x3_zp(const vpt_conv_zp_args* args, void* stream);
+/* 1 (default): SM pairs cooperate on 256-row tiles with tcgen05.mma.cta_group::2 (each CTA stages half of the weight
+ * tile); 0: one CTA per tile.  Tuning / A-B knob. */
+int vpt_set_conv_pair_mode(int32_t on);
 int vpt_conv_zp_stat_parts(int32_t Cout);
 
 /* ----------------------------------------------------------------------------------------------------------

@@ -120,15 +120,20 @@ def test_conv3x3_zp(H, W, Cin, Cout, F_):
     mr = torch.stack([torch.randn(F_, generator=g) * 0.3, torch.rand(F_, generator=g) + 0.5], 1)
     S1, S2 = torch.randn(9, Cout, generator=g), torch.randn(9, Cout, generator=g)
     res = E.to_zp(_rand((F_, H, W, Cout), g))
-    for residual in (None, res):
-        got, gmr = ops.conv3x3_zp(x.to(DEV), Wb.to(DEV), H, W, mr=mr.to(DEV), S1=S1.to(DEV), S2=S2.to(DEV), relu=1,
-                                  residual=None if residual is None else residual.to(DEV))
-        nat.device_check()
-        ref, rmr = E.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, residual=residual)
-        gc = got.cpu()
-        assert (gc[:, -1] == 0).all() and (gc[:, :, -1] == 0).all(), "ZP zero row/column not maintained by the conv epilogue"
-        _close(f"conv3x3_zp {F_}x{H}x{W} {Cin}->{Cout} res={residual is not None}", got, ref)
-        _close("conv3x3_zp stats", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
+    try:
+        for pair in (0, 1):  # one CTA per tile / SM pairs with tcgen05.mma.cta_group::2
+            nat.lib().vpt_set_conv_pair_mode(pair)
+            for residual in (None, res):
+                got, gmr = ops.conv3x3_zp(x.to(DEV), Wb.to(DEV), H, W, mr=mr.to(DEV), S1=S1.to(DEV), S2=S2.to(DEV), relu=1,
+                                          residual=None if residual is None else residual.to(DEV))
+                nat.device_check()
+                ref, rmr = E.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, residual=residual)
+                gc = got.cpu()
+                assert (gc[:, -1] == 0).all() and (gc[:, :, -1] == 0).all(), "ZP zero row/column not maintained by the conv epilogue"
+                _close(f"conv3x3_zp pair={pair} {F_}x{H}x{W} {Cin}->{Cout} res={residual is not None}", got, ref)
+                _close(f"conv3x3_zp stats pair={pair}", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
+    finally:
+        nat.lib().vpt_set_conv_pair_mode(1)
 
 
 def test_zp_pool_norm():

@@ -6,7 +6,6 @@ import torch
 import vpt_b200
 from video_pre_training_b200 import _native as nat, ops
 l = nat.lib()
-l.vpt_debug_set.argtypes = [ctypes.c_int32, ctypes.c_int32]
 g = torch.Generator().manual_seed(0)
 M, N, K = 512, 128, 256
 A = torch.randn(M, K, generator=g).to(torch.bfloat16)

@@ -34,7 +34,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 
 records = []
-names = ["gemm", "stats_finalize", "firstconv_pool", "maxpool3s2", "affine_norm", "copy_rows", "state_mask_update", "attention", "log_softmax"]
+names = ["gemm", "conv3x3_zp", "stats_finalize", "firstconv_pool", "maxpool3s2", "affine_norm", "affine_norm_zp", "copy_rows", "state_mask_update", "attention", "log_softmax"]
 orig = {n: getattr(ops, n) for n in names}
 
 
@@ -51,6 +51,10 @@ def wrap(n):
             M, N, K = args[3], args[4], args[5]
             tag = f"gemm {'conv' if kw.get('conv') is not None else 'lin'} N={N} K={K}" + (f" HW={kw['conv'][0]}" if kw.get("conv") is not None else "")
             records.append((tag, e0, e1, 2.0 * M * N * K))
+        elif n == "conv3x3_zp":
+            x, Wb, H, W = args[0], args[1], args[2], args[3]
+            tag = f"conv_zp N={Wb.shape[0]} K={Wb.shape[1]} HW={H}" + (" +res" if kw.get("residual") is not None else "")
+            records.append((tag, e0, e1, 2.0 * x.shape[0] * H * W * Wb.shape[0] * Wb.shape[1]))
         else:
             records.append((tag, e0, e1, 0.0))
         return r
@@ -73,7 +77,7 @@ for tag, e0, e1, f in records:
     cnt[tag] += 1
     fl[tag] += f
 step = s0.elapsed_time(s1)
-print(f"step {step:.1f} ms  ({B*T/step*1000:.0f} frames/s) ; note: firstconv_pool/maxpool3s2/affine_norm include their stats_finalize")
+print(f"step {step:.1f} ms  ({B*T/step*1000:.0f} frames/s) ; note: firstconv_pool/maxpool3s2/affine_norm*/conv3x3_zp include their stats_finalize")
 for k, v in sorted(tot.items(), key=lambda x: -x[1]):
     extra = f"  {fl[k]/v/1e9:8.0f} TFLOP/s" if fl[k] else ""
     print(f"{v:9.2f} ms {100*v/step:5.1f}%  n={cnt[k]:4d}  {k}{extra}")

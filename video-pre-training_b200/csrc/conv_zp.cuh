@@ -23,6 +23,8 @@
 
 namespace vpt {
 
+static int g_cz_pair = 1;
+
 constexpr int kCzThreads = 96 + 32 * kNumEpiWarps;  // 11 warps
 constexpr int kCzMaxBStages = 8;
 
@@ -42,12 +44,19 @@ struct ConvZpParams {
     float* stat_part;  // [Q][2 * num_n_tiles] float2 or null
 };
 
+// kPair: two CTAs of a cluster (an SM pair) cooperate on a 256-row tile with tcgen05.mma.cta_group::2 -- each CTA stages
+// its own 128 input rows and HALF of the weight tile, so the shared-memory operand traffic per FLOP (the measured limiter
+// of single-CTA UMMA) is halved for the weights.
+template <bool kPair>
 __global__ void __launch_bounds__(kCzThreads, 1)
 conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvZpParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    const uint32_t b_stage_bytes = (uint32_t)p.block_n * kBlockK * 2;
+    const uint32_t b_rows = (uint32_t)p.block_n / (kPair ? 2 : 1);   // weight rows staged by this CTA
+    const uint32_t b_stage_bytes = b_rows * kBlockK * 2;
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = (cta_rank == 0);
     uint8_t* smem_a = smem;                                        // 2 A-span stages
     uint8_t* smem_b = smem + 2 * (size_t)p.a_stage_bytes;          // b_stages weight tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_stage_bytes);
@@ -69,7 +78,7 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+            mbar_init(&tmem_empty_bar[i], kNumEpiWarps * (kPair ? 2 : 1));  // pair: both CTAs' epilogues release the leader's MMA
         }
         for (int i = 0; i < p.b_stages; ++i) {
             mbar_init(&b_full[i], 1);
@@ -78,16 +87,25 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, 512);
-        tmem_relinquish();
+        if (kPair) {
+            tmem_alloc_pair(tmem_ptr_smem, 512);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr_smem, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (kPair) cluster_sync_all();  // the peer's barriers exist before anything is signalled across the pair
 
-    const long long num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int tile_rows = p.mt * kBlockM;
+    const long long num_tiles = p.num_m_tiles * p.num_n_tiles;   // pair mode: tiles of 256 rows, 128 per CTA
+    const int tile_rows = p.mt * kBlockM * (kPair ? 2 : 1);
+    const int cta_row0 = kPair ? (int)cta_rank * kBlockM : 0;      // this CTA's first row inside a tile
+    const long long tile_begin = kPair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+    const long long tile_step = kPair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
     const int halo = p.Wp + 1;  // rows before / after the tile that the taps reach
 
     if (warp == 0) {
@@ -96,15 +114,18 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+            for (long long tile = tile_begin; tile < num_tiles && ok; tile += tile_step) {
                 const long long m_tile = tile / p.num_n_tiles;
-                const long long span0 = m_tile * tile_rows - halo;
+                const long long span0 = m_tile * tile_rows + cta_row0 - halo;
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     if (!(ok = mbar_wait(&a_empty[stage], phase ^ 1u, 0x110u))) break;
-                    mbar_expect_tx(&a_full[stage], (uint32_t)p.a_stage_bytes);
+                    // pair: the leader's barrier collects the bytes of BOTH CTAs' spans
+                    if (leader) mbar_expect_tx(&a_full[stage], (uint32_t)p.a_stage_bytes * (kPair ? 2u : 1u));
                     uint8_t* sa = smem_a + (size_t)stage * p.a_stage_bytes;
-                    for (int b = 0; b < p.a_boxes; ++b)
-                        tma_load_2d(sa + (size_t)b * p.a_box_rows * 128, &tmA, &a_full[stage], cb * kBlockK, (int)(span0 + (long long)b * p.a_box_rows));
+                    for (int b = 0; b < p.a_boxes; ++b) {
+                        if (kPair) tma_load_2d_pair(sa + (size_t)b * p.a_box_rows * 128, &tmA, &a_full[stage], cb * kBlockK, (int)(span0 + (long long)b * p.a_box_rows));
+                        else tma_load_2d(sa + (size_t)b * p.a_box_rows * 128, &tmA, &a_full[stage], cb * kBlockK, (int)(span0 + (long long)b * p.a_box_rows));
+                    }
                     advance(stage, phase, 2);
                 }
             }
@@ -115,27 +136,28 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const int n0 = (int)(tile % p.num_n_tiles) * p.block_n;
+            for (long long tile = tile_begin; tile < num_tiles && ok; tile += tile_step) {
+                const int n0 = (int)(tile % p.num_n_tiles) * p.block_n + (int)(cta_rank * b_rows);  // pair: this CTA's half of the rows
                 for (int cb = 0; cb < p.cin_blocks && ok; ++cb) {
                     for (int tap = 0; tap < 9; ++tap) {
                         if (!(ok = mbar_wait(&b_empty[stage], phase ^ 1u, 0x120u))) break;
-                        mbar_expect_tx(&b_full[stage], b_stage_bytes);
-                        tma_load_2d(smem_b + (size_t)stage * b_stage_bytes, &tmB, &b_full[stage], tap * p.cin + cb * kBlockK, n0);
+                        if (leader) mbar_expect_tx(&b_full[stage], b_stage_bytes * (kPair ? 2u : 1u));
+                        if (kPair) tma_load_2d_pair(smem_b + (size_t)stage * b_stage_bytes, &tmB, &b_full[stage], tap * p.cin + cb * kBlockK, n0);
+                        else tma_load_2d(smem_b + (size_t)stage * b_stage_bytes, &tmB, &b_full[stage], tap * p.cin + cb * kBlockK, n0);
                         advance(stage, phase, p.b_stages);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n);
+        if (lane == 0 && leader) {
+            // ================= MMA issuer (pair: the leader CTA issues for both SMs) =================
+            const uint32_t idesc = umma_idesc_bf16(kPair ? 2 * kBlockM : kBlockM, p.block_n);
             int astage = 0, bstage = 0;
             uint32_t aphase_s = 0, bphase = 0;
             int local = 0;
             bool ok = true;
-            for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
+            for (long long tile = tile_begin; tile < num_tiles && ok; tile += tile_step, ++local) {
                 const int as = local & 1;
                 const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
                 if (!(ok = mbar_wait(&tmem_empty_bar[as], accphase ^ 1u, 0x210u))) break;
@@ -150,21 +172,34 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         tc_fence_after();
                         const uint32_t b_addr = smem_u32(smem_b + (size_t)bstage * b_stage_bytes);
                         const int row_off = (tap / 3) * p.Wp + (tap % 3);  // (dy+1)*Wp + (dx+1)
-                        for (int j = 0; j < p.mt; ++j) {
-                            const uint32_t a_addr = a_base + (uint32_t)(row_off + j * kBlockM) * 128u;
+                        if (kPair) {
+                            const uint32_t a_addr = a_base + (uint32_t)row_off * 128u;
 #pragma unroll
                             for (int k = 0; k < kBlockK / 16; ++k)
-                                umma_bf16(d_tmem + (uint32_t)(j * p.block_n), umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
-                                          idesc, (uint32_t)((cb | tap | k) != 0));
+                                umma_bf16_pair(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                               (uint32_t)((cb | tap | k) != 0));
+                        } else {
+                            for (int j = 0; j < p.mt; ++j) {
+                                const uint32_t a_addr = a_base + (uint32_t)(row_off + j * kBlockM) * 128u;
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k)
+                                    umma_bf16(d_tmem + (uint32_t)(j * p.block_n), umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
+                                              idesc, (uint32_t)((cb | tap | k) != 0));
+                            }
                         }
-                        umma_commit(&b_empty[bstage]);
+                        if (kPair) umma_commit_pair(&b_empty[bstage], 3);  // frees the slot in both CTAs
+                        else umma_commit(&b_empty[bstage]);
                         advance(bstage, bphase, p.b_stages);
                     }
                     if (!ok) break;
-                    umma_commit(&a_empty[astage]);
+                    if (kPair) umma_commit_pair(&a_empty[astage], 3);
+                    else umma_commit(&a_empty[astage]);
                     advance(astage, aphase_s, 2);
                 }
-                if (ok) umma_commit(&tmem_full_bar[as]);
+                if (ok) {
+                    if (kPair) umma_commit_pair(&tmem_full_bar[as], 3);  // both CTAs' epilogues read their own 128 rows
+                    else umma_commit(&tmem_full_bar[as]);
+                }
             }
         }
     } else {
@@ -180,13 +215,13 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool tab_vec = ((p.N & 3) == 0);
         int local = 0;
         bool ok = true;
-        for (long long tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local) {
+        for (long long tile = tile_begin; tile < num_tiles && ok; tile += tile_step, ++local) {
             const long long m_tile = tile / p.num_n_tiles;
             const int n_tile = (int)(tile % p.num_n_tiles);
             const int n0 = n_tile * p.block_n;
             const int as = local & 1;
             const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
-            const long long q = m_tile * tile_rows + sub * kBlockM + quarter * 32 + lane;
+            const long long q = m_tile * tile_rows + cta_row0 + sub * kBlockM + quarter * 32 + lane;
             const bool row_ok = q < p.Q;
             // decode the ZP row: frame, y, x
             const long long f = q / p.FS;
@@ -296,7 +331,10 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            if (lane == 0) {
+                if (kPair) mbar_arrive_cluster(&tmem_empty_bar[as], 0);  // the leader's MMA thread waits on its own barrier
+                else mbar_arrive(&tmem_empty_bar[as]);
+            }
             if (p.stat_part && row_ok) {
                 float2* sp = reinterpret_cast<float2*>(p.stat_part) + (size_t)q * P + n_tile * 2;
                 if (p.mt == 2) {
@@ -311,9 +349,11 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (kPair) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -334,15 +374,17 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.Q < 2147483647LL, "vpt_conv3x3_zp: too many rows for 32-bit TMA coordinates");
     p.N = N; p.cin = C; p.cin_blocks = C / 64;
     choose_block_n(N, &p.block_n, &p.num_n_tiles);
-    p.mt = (p.block_n <= 128) ? 2 : 1;
-    const int tile_rows = p.mt * kBlockM;
+    const bool pair = (g_cz_pair != 0) && (p.block_n % 16 == 0) && (p.Q > 256);
+    p.mt = (!pair && p.block_n <= 128) ? 2 : 1;
+    const int cta_rows = p.mt * kBlockM;                  // rows per CTA per tile
+    const int tile_rows = cta_rows * (pair ? 2 : 1);
     p.num_m_tiles = (p.Q + tile_rows - 1) / tile_rows;
-    const int span = tile_rows + 2 * (p.Wp + 1);
+    const int span = cta_rows + 2 * (p.Wp + 1);
     p.a_boxes = (span + 255) / 256;
     p.a_box_rows = ((span + p.a_boxes - 1) / p.a_boxes + 7) / 8 * 8;
     VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
     p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
-    const uint32_t b_stage_bytes = (uint32_t)p.block_n * kBlockK * 2;
+    const uint32_t b_stage_bytes = (uint32_t)(p.block_n / (pair ? 2 : 1)) * kBlockK * 2;
     const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - 512;
     int bst = (int)(budget / b_stage_bytes);
     if (bst > kCzMaxBStages) bst = kCzMaxBStages;
@@ -361,7 +403,7 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     {
         cuuint64_t dims[2] = {(cuuint64_t)9 * C, (cuuint64_t)N};
         cuuint64_t strides[1] = {(cuuint64_t)9 * C * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)p.block_n};
+        cuuint32_t box[2] = {64, (cuuint32_t)(p.block_n / (pair ? 2 : 1))};
         int r = make_tmap_bf16(&tmB, a->w, 2, dims, strides, box);
         if (r) return r;
     }
@@ -373,15 +415,51 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const long long tiles = p.num_m_tiles * p.num_n_tiles;
-    long long grid = num_sms();
-    if (grid <= 0) grid = 148;
-    if (grid > tiles) grid = tiles;
-    conv3x3_zp_kernel<<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
-    VPT_LAUNCH_CHECK();
+    if (!pair) {
+        long long grid = num_sms();
+        if (grid <= 0) grid = 148;
+        if (grid > tiles) grid = tiles;
+        conv3x3_zp_kernel<false><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+        VPT_LAUNCH_CHECK();
+        return VPT_OK;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(kCzThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_pairs = 0;
+    if (max_pairs == 0) {
+        int n = 0;
+        cfg.gridDim = dim3(num_sms() / 2 * 2);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv3x3_zp_kernel<true>, &cfg);
+        if (e != cudaSuccess || n <= 0) {
+            (void)cudaGetLastError();
+            n = num_sms() / 2;
+        }
+        max_pairs = n;
+    }
+    long long pairs = max_pairs;
+    if (pairs > tiles) pairs = tiles;
+    cfg.gridDim = dim3((unsigned)(pairs * 2));
+    VPT_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_zp_kernel<true>, tmA, tmB, p));
+    return VPT_OK;
+}
+
+extern "C" int vpt_set_conv_pair_mode(int32_t on) {
+    vpt::g_cz_pair = on ? 1 : 0;
     return VPT_OK;
 }
 
