@@ -112,8 +112,8 @@ typedef struct vpt_conv_zp_args {
 } vpt_conv_zp_args;
 
 int vpt_conv3x3_zp(const vpt_conv_zp_args* args, void* stream);
-/* 1 (default): SM pairs cooperate on 256-row tiles with tcgen05.mma.cta_group::2 (each CTA stages half of the weight
- * tile); 0: one CTA per tile.  Tuning / A-B knob. */
+/* SM pairs cooperating on 256-row tiles with tcgen05.mma.cta_group::2 (each CTA stages half of the weight tile):
+ * 0 = never, 1 = auto (default: pairs when Cout > 128, where they measure +11-13 %), 2 = always.  Tuning / A-B knob. */
 int vpt_set_conv_pair_mode(int32_t on);
 int vpt_conv_zp_stat_parts(int32_t Cout);
 

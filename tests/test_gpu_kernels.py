@@ -121,7 +121,7 @@ def test_conv3x3_zp(H, W, Cin, Cout, F_):
     S1, S2 = torch.randn(9, Cout, generator=g), torch.randn(9, Cout, generator=g)
     res = E.to_zp(_rand((F_, H, W, Cout), g))
     try:
-        for pair in (0, 1):  # one CTA per tile / SM pairs with tcgen05.mma.cta_group::2
+        for pair in (0, 2):  # one CTA per tile / SM pairs with tcgen05.mma.cta_group::2
             nat.lib().vpt_set_conv_pair_mode(pair)
             for residual in (None, res):
                 got, gmr = ops.conv3x3_zp(x.to(DEV), Wb.to(DEV), H, W, mr=mr.to(DEV), S1=S1.to(DEV), S2=S2.to(DEV), relu=1,

@@ -374,7 +374,9 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.Q < 2147483647LL, "vpt_conv3x3_zp: too many rows for 32-bit TMA coordinates");
     p.N = N; p.cin = C; p.cin_blocks = C / 64;
     choose_block_n(N, &p.block_n, &p.num_n_tiles);
-    const bool pair = (g_cz_pair != 0) && (p.block_n % 16 == 0) && (p.Q > 256);
+    // measured (tools/conv_bench.py): SM pairs win for 256-wide weight tiles (+11-13 %), a single CTA with two 128-row
+    // sub-tiles wins for <= 128 output channels; g_cz_pair: 0 = never, 1 = auto, 2 = always
+    const bool pair = (g_cz_pair == 2 || (g_cz_pair == 1 && p.block_n > 128)) && (p.block_n % 16 == 0) && (p.Q > 256);
     p.mt = (!pair && p.block_n <= 128) ? 2 : 1;
     const int cta_rows = p.mt * kBlockM;                  // rows per CTA per tile
     const int tile_rows = cta_rows * (pair ? 2 : 1);
@@ -459,7 +461,7 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
 }
 
 extern "C" int vpt_set_conv_pair_mode(int32_t on) {
-    vpt::g_cz_pair = on ? 1 : 0;
+    vpt::g_cz_pair = on;
     return VPT_OK;
 }
 
