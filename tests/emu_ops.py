@@ -108,17 +108,22 @@ def _frame_stats(x_interior):
     return _row_stats(x_interior.reshape(x_interior.shape[0], -1), 1)
 
 
-def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True):
+def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True, out=None):
     F_, Cin = x.shape[0], x.shape[3]
     Cout = Wb.shape[0]
     assert (x[:, -1] == 0).all() and (x[:, :, -1] == 0).all(), "ZP invariant violated on the conv input"
     xi = from_zp(x).contiguous()
     M = F_ * H * W
+    out_buf = out
     out = torch.zeros((M, Cout), dtype=BF16)
     gemm(xi, Wb, out, M, Cout, 9 * Cin, conv=(H, W, Cin), mr=mr, rows_per_group=H * W, S1=S1, S2=S2, relu=relu,
          residual=None if residual is None else from_zp(residual).contiguous())
     o = out.reshape(F_, H, W, Cout)
-    return to_zp(o), (_frame_stats(o) if want_stats else None)
+    res = to_zp(o)
+    if out_buf is not None:
+        out_buf.copy_(res)
+        res = out_buf
+    return res, (_frame_stats(o) if want_stats else None)
 
 
 def firstconv_pool(img, w, bias, C0, zp=True):

@@ -81,13 +81,15 @@ def stats_finalize(part, G, n_per_group, count, eps=1e-5):
     return mr
 
 
-def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True):
+def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True, out=None):
     """GroupNorm(1)->conv3x3->ReLU[+residual] on a ZP tensor x bf16 [F,H+1,W+1,Cin]; returns (ZP out, per-frame (mean, rstd))."""
     _cuda(x, Wb)
     F_, Cin = x.shape[0], x.shape[3]
     Cout = Wb.shape[0]
     assert tuple(x.shape[1:3]) == (H + 1, W + 1) and Wb.shape[1] == 9 * Cin
-    out = torch.empty((F_, H + 1, W + 1, Cout), dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty((F_, H + 1, W + 1, Cout), dtype=BF16, device=x.device)
+    assert out.is_contiguous() and tuple(out.shape) == (F_, H + 1, W + 1, Cout)
     P = nat.lib().vpt_conv_zp_stat_parts(Cout)
     part = torch.empty((F_ * (H + 1) * (W + 1), P, 2), dtype=F32, device=x.device) if want_stats else None
     a = nat.ConvZpArgs()

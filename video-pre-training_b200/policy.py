@@ -295,8 +295,9 @@ class MinecraftPolicy(nn.Module):
     # -- CNN -----------------------------------------------------------------------------------------------
     # Activations are kept in the "ZP" layout [F][H+1][W+1][C] (zero last row / column; include/vpt_b200.h): it lets the
     # conv kernel address every 3x3 neighbour linearly and reuse one shared-memory input span for all nine taps.
-    def _cnn_chunk(self, img, prep: _Prepared, pfx="img_process.cnn"):
-        """lib/impala_cnn.py:187-195 for a chunk of frames; returns (x ZP [F, Hf+1, Wf+1, C2] bf16, per-frame stats)."""
+    def _cnn_chunk(self, img, prep: _Prepared, out, pfx="img_process.cnn"):
+        """lib/impala_cnn.py:187-195 for a chunk of frames; writes the last stack's output (ZP [F, Hf+1, Wf+1, C2] bf16) into
+        `out` and returns (out, per-frame stats)."""
         cfg = self.cfg
         H, W = cfg.img_shape[0], cfg.img_shape[1]
         x, mr = None, None
@@ -320,7 +321,8 @@ class MinecraftPolicy(nn.Module):
                 hmid, mrh = ops.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1)
                 self._tap(f"{pfx}.stacks.{i}.blocks.{j}.conv0", hmid)
                 Wb, S1, S2 = st["convs"][2 * j + 1]
-                x, mr = ops.conv3x3_zp(hmid, Wb, H, W, mr=mrh, S1=S1, S2=S2, relu=1, residual=x)
+                last = (i == len(cfg.chans) - 1) and j == 1
+                x, mr = ops.conv3x3_zp(hmid, Wb, H, W, mr=mrh, S1=S1, S2=S2, relu=1, residual=x, out=out if last else None)
                 self._tap(f"{pfx}.stacks.{i}.blocks.{j}", x)
         return x, mr
 
@@ -394,19 +396,17 @@ class MinecraftPolicy(nn.Module):
         first_u8 = first.to(device=img.device, dtype=torch.bool).contiguous().view(torch.uint8)
         Hf, Wf = cfg.final_hw
         C2 = cfg.chans[-1]
-        # ---- ImpalaCNN + dense, in frame chunks
-        xd = torch.empty((N, cfg.cnn_outsize), dtype=BF16, device=img.device)
-        Pd = ops.gemm_stat_parts(cfg.cnn_outsize)
-        part_d = torch.empty((N, Pd, 2), dtype=F32, device=img.device)
-        Wd, S1d, S2d = prep.dense
+        # ---- ImpalaCNN in frame chunks (bounds the activation workspace), then ONE dense GEMM over all frames
+        cnn_out = torch.empty((N, Hf + 1, Wf + 1, C2), dtype=BF16, device=img.device)
+        mrs = []
         for f0 in range(0, N, self.cnn_chunk_frames):
             F_ = min(self.cnn_chunk_frames, N - f0)
-            x, mr = self._cnn_chunk(frames[f0:f0 + F_], prep)
-            Kd = (Hf + 1) * (Wf + 1) * C2  # ZP rows flattened; the zero row / column meets zero weight columns
-            ops.gemm(x.view(F_, Kd), Wd, xd[f0:f0 + F_], F_, cfg.cnn_outsize, Kd, mr=mr, rows_per_group=1,
-                     S1=S1d, S2=S2d, relu=1, stat_part=part_d[f0:f0 + F_], stat_mode=1)
-            del x, mr
-        mr_d = ops.stats_finalize(part_d, N, Pd, cfg.cnn_outsize)
+            _, mr = self._cnn_chunk(frames[f0:f0 + F_], prep, cnn_out[f0:f0 + F_])
+            mrs.append(mr)
+        mr_c = mrs[0] if len(mrs) == 1 else torch.cat(mrs, 0)
+        Kd = (Hf + 1) * (Wf + 1) * C2  # ZP rows flattened; the zero row / column meets zero weight columns
+        xd, mr_d = self._linear(cnn_out.view(N, Kd), prep.dense, cfg.cnn_outsize, mr=mr_c, relu=1, want_stats=True)
+        del cnn_out
         self._tap("img_process.cnn.dense", xd)
         x, mr_x = self._linear(xd, prep.linear, cfg.hidsize, mr=mr_d, relu=1, want_stats=True)
         self._tap("img_process", x)
