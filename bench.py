@@ -28,6 +28,9 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 import torch  # noqa: E402
 
 METRIC = "frames/sec MinecraftPolicy fwd, 128x128x3 BxT=128x128"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (conv3x3_zp_kernel, 128->128 @64x64, 2048 frames)
+# from the committed `ncu --set full` capture (profiles/conv_zp_r1.md); null until measured
+TRAFFIC_NCU = None
 
 
 def parse():
@@ -225,7 +228,8 @@ def run_ours(args):
     cfg = O.Cfg(**kw)
     flops_frame = O.forward_flops_per_frame(cfg)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                "traffic": None, "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv3x3 + linear)", "peak_source": pk["source"],
+                "traffic": TRAFFIC_NCU, "kernel": "conv3x3_zp_kernel + gemm_tc_kernel (tcgen05 implicit-GEMM conv3x3 / linear)",
+                "peak_source": pk["source"],
                 "launches_per_step": len(prof) // args.steps, "kernel_ms_per_step": g_ms / args.steps,
                 "kernel_share_of_step": g_ms / ms if world == 1 else None,
                 "algorithmic_gflop_per_frame": flops_frame / 1e9, "gemm_gflop_per_frame": g_fl / args.steps / frames_per_step / 1e9,

@@ -57,6 +57,41 @@ __global__ void stats_finalize_kernel(const float2* __restrict__ part, float2* _
     }
 }
 
+// large groups (a conv frame has thousands of per-row partials): one 256-thread block per group, fixed-order tree
+__global__ void __launch_bounds__(256) stats_finalize_block_kernel(const float2* __restrict__ part, float2* __restrict__ mr, int n_per_group,
+                                                                     double inv_count, float eps) {
+    __shared__ double red[2][8];
+    const long long g = blockIdx.x;
+    const float2* p = part + g * (long long)n_per_group;
+    double s = 0.0, ss = 0.0;
+    for (int i = threadIdx.x; i < n_per_group; i += 256) {
+        const float2 v = __ldg(p + i);
+        s += (double)v.x;
+        ss += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = ss = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            s += red[0][w];
+            ss += red[1][w];
+        }
+        const double mean = s * inv_count;
+        double var = ss * inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // max_pool2d(3, 2, 1) on non-negative NHWC bf16; 8 channels (16 B) per thread; grid = (blocks_per_frame, F)
 // ---------------------------------------------------------------------------------------------------------
@@ -255,6 +290,12 @@ extern "C" int vpt_stats_finalize(const float* stat_part, float* mr, int64_t G, 
                                   void* stream) {
     using namespace vpt;
     VPT_CHECK(stat_part && mr && G > 0 && n_per_group > 0 && count > 0, "vpt_stats_finalize: bad arguments");
+    if (n_per_group >= 512) {
+        stats_finalize_block_kernel<<<(unsigned)G, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(stat_part),
+                                                                                   reinterpret_cast<float2*>(mr), n_per_group, 1.0 / count, eps);
+        VPT_LAUNCH_CHECK();
+        return VPT_OK;
+    }
     const int wpb = 8;
     const long long blocks = (G + wpb - 1) / wpb;
     stats_finalize_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
