@@ -128,6 +128,14 @@ int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, vo
                        int32_t F, int32_t H, int32_t W, int32_t C0, int32_t zp, void* stream);
 int vpt_firstconv_stat_parts(int32_t H, int32_t W);
 
+/* IDM temporal pre-stage (lib/policy.py:394-403 + :39-45): u8 -> /255 -> Conv3d(3 -> C, kernel (5,1,1), pad (2,0,0)) + bias -> ReLU,
+ * per sample over its T frames (zero padded in time at the chunk ends, like the reference's per-sample loop).
+ *   img u8 [B][T][H][W][3]   w fp32 [C][15] ordered (dt, c), already divided by 255   out bf16 ZP [B*T][H+1][W+1][C]
+ *   stat_part float2 [B*T][vpt_conv3d_stat_parts(H, W, C)] */
+int vpt_conv3d_t5(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part, int32_t B, int32_t T,
+                  int32_t H, int32_t W, int32_t C, void* stream);
+int vpt_conv3d_stat_parts(int32_t H, int32_t W, int32_t C);
+
 /* max_pool2d(kernel 3, stride 2, pad 1) on a non-negative NHWC bf16 tensor (lib/impala_cnn.py:117).
  *   in [F][H][W][C] -> out [F][H/2][W/2][C]   (zp=1: both in the ZP layout, [F][H+1][W+1][C] -> [F][H/2+1][W/2+1][C])
  *   stat_part float2 [F][vpt_pool_stat_parts()] */

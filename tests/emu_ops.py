@@ -135,6 +135,15 @@ def firstconv_pool(img, w, bias, C0, zp=True):
     return (to_zp(y) if zp else y), _frame_stats(y)
 
 
+def conv3d_t5(img, w, bias, C):
+    B, T, H, W, _ = img.shape
+    x = img.float().permute(0, 4, 1, 2, 3)                       # b c t h w
+    wt = w.reshape(C, 5, 3).permute(0, 2, 1).reshape(C, 3, 5, 1, 1)  # [C][dt][c] -> [C][c][dt][1][1]
+    y = F.relu(F.conv3d(x, wt, bias, padding=(2, 0, 0)))         # per-sample zero padding in time == batched conv3d
+    y = y.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, C).contiguous().to(BF16)
+    return to_zp(y), _frame_stats(y)
+
+
 def maxpool3s2(x, zp=True):
     xi = from_zp(x) if zp else x
     y = F.max_pool2d(xi.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)

@@ -20,6 +20,7 @@ void set_error(const char* fmt, ...) {
 #include "conv_zp.cuh"
 #include "elementwise.cuh"
 #include "firstconv.cuh"
+#include "conv3d.cuh"
 #include "attention.cuh"
 #include "heads.cuh"
 

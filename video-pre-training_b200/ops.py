@@ -121,6 +121,18 @@ def firstconv_pool(img, w, bias, C0, zp=True):
     return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * C0)
 
 
+def conv3d_t5(img, w, bias, C):
+    """img u8 [B,T,H,W,3] -> (bf16 ZP [B*T,H+1,W+1,C], per-frame (mean, rstd)); lib/policy.py:394-403."""
+    _cuda(img, w, bias)
+    B, T, H, W, _ = img.shape
+    out = torch.empty((B * T, H + 1, W + 1, C), dtype=BF16, device=img.device)
+    P = nat.lib().vpt_conv3d_stat_parts(H, W, C)
+    part = torch.empty((B * T, P, 2), dtype=F32, device=img.device)
+    nat.check(nat.lib().vpt_conv3d_t5(_p(img), _p(w), _p(bias), _p(out), _p(part), B, T, H, W, C, _stream()), "vpt_conv3d_t5")
+    _count()
+    return out, stats_finalize(part, B * T, P, H * W * C)
+
+
 def maxpool3s2(x, zp=True):
     """bf16 [F,H,W,C] (>= 0) -> (bf16 [F,H/2,W/2,C], per-frame (mean, rstd)); with zp both tensors are ZP ([F,H+1,W+1,C])."""
     _cuda(x)

@@ -72,7 +72,8 @@ class NetConfig:
                  init_norm_kwargs=None, impala_kwargs=None, input_shape=None, active_reward_monitors=None, img_statistics=None,
                  first_conv_norm=False, diff_mlp_embedding=False, attention_mask_style="clipped_causal", attention_heads=8,
                  attention_memory_size=2048, use_pointwise_layer=True, pointwise_ratio=4, pointwise_use_activation=False,
-                 n_recurrence_layers=1, recurrence_is_residual=True, timesteps=None, use_pre_lstm_ln=True, **unused_kwargs):
+                 n_recurrence_layers=1, recurrence_is_residual=True, timesteps=None, use_pre_lstm_ln=True, conv3d_params=None,
+                 **unused_kwargs):
         init_norm_kwargs = init_norm_kwargs or {}
         impala_kwargs = impala_kwargs or {}
         # Only the configuration family of the released models is implemented in CUDA; anything else is refused loudly.
@@ -99,6 +100,14 @@ class NetConfig:
         self.img_shape = tuple(img_shape)
         self.pointwise_ratio = pointwise_ratio
         self.single_output = single_output
+        # IDM (lib/policy.py:342-372): a temporal conv3d pre-stage feeds the CNN, whose first conv is then normalised too
+        self.conv3d_out = None
+        if conv3d_params is not None:
+            ks, pad = list(conv3d_params.get("kernel_size", [])), list(conv3d_params.get("padding", []))
+            if conv3d_params.get("inchan") != 3 or ks != [5, 1, 1] or pad != [2, 0, 0]:
+                raise NotImplementedError("vpt_b200: conv3d_params must be inchan=3, kernel_size=[5,1,1], padding=[2,0,0] (the IDM)")
+            self.conv3d_out = int(conv3d_params["outchan"])
+            first_conv_norm = True
         self.first_conv_norm = first_conv_norm
         self.cnn_outsize = 256
         assert hidsize % attention_heads == 0, "Embsize must be divisible by number of heads"  # lib/xf.py:98
@@ -106,8 +115,11 @@ class NetConfig:
             raise NotImplementedError("vpt_b200: head_dim must be 128 (true of every VPT width)")
         assert self.maxlen > 0 or self.mask_style == "none"  # lib/xf.py:256
         H, W, Cin = self.img_shape
-        if Cin != 3 or H % 16 or W % 16 or any(c % 64 for c in self.chans):
-            raise NotImplementedError("vpt_b200: img must be (H,W,3) with H,W %% 16 == 0 and CNN channels %% 64 == 0")
+        want_cin = 3 if self.conv3d_out is None else self.conv3d_out
+        if Cin != want_cin or H % 16 or W % 16 or any(c % 64 for c in self.chans) or (self.conv3d_out or 64) % 64:
+            raise NotImplementedError("vpt_b200: img must be (H,W,3) [(H,W,conv3d outchan) for the IDM] with H,W % 16 == 0 and channels % 64 == 0")
+        if self.first_conv_norm and self.conv3d_out is None:
+            raise NotImplementedError("vpt_b200: first_conv_norm without the conv3d pre-stage is not implemented")
         self.final_hw = (H // 8, W // 8)
 
 
@@ -158,6 +170,9 @@ def _net_schema(cfg: NetConfig) -> "OrderedDict[str, torch.Tensor]":
     sd["lastlayer.norm.weight"], sd["lastlayer.norm.bias"] = torch.ones(h), torch.zeros(h)
     sd["lastlayer.layer.weight"] = _fanin((h, h), 1.0)
     sd["final_ln.weight"], sd["final_ln.bias"] = torch.ones(h), torch.zeros(h)
+    if cfg.conv3d_out is not None:  # lib/policy.py:362-372 (registered after the base class's modules)
+        sd["conv3d_layer.layer.weight"] = _fanin((cfg.conv3d_out, 3, 5, 1, 1), 1.0)
+        sd["conv3d_layer.layer.bias"] = torch.zeros(cfg.conv3d_out)
     return sd
 
 
@@ -201,6 +216,10 @@ class _Prepared:
     def __init__(self, cfg: NetConfig, sd: Dict[str, torch.Tensor], prefix: str = ""):
         g = lambda k: sd[prefix + k].detach()
         p = "img_process.cnn"
+        self.conv3d = None
+        if cfg.conv3d_out is not None:  # [C, 3, dt, 1, 1] -> [C][dt][c] / 255
+            w3 = g("conv3d_layer.layer.weight").double().reshape(cfg.conv3d_out, 3, 5).permute(0, 2, 1).reshape(cfg.conv3d_out, 15) / 255.0
+            self.conv3d = (w3.float().contiguous(), g("conv3d_layer.layer.bias").float().contiguous())
         self.stacks = []
         for i, c in enumerate(cfg.chans):
             s = f"{p}.stacks.{i}"
@@ -258,6 +277,7 @@ class MinecraftPolicy(nn.Module):
     """lib/policy.py:83-224.  `forward(ob, state_in, context)` -> ((pi_latent, vf_latent), state_out)."""
 
     cnn_chunk_frames = 2048  # frames per CNN pass (bounds the activation workspace: ~5 MiB/frame at 2x width)
+    idm_chunk_frames = 512   # IDM: ~13 MiB/frame at 4x width (conv3d output + full-resolution first conv)
 
     def __init__(self, **policy_kwargs):
         super().__init__()
@@ -301,6 +321,9 @@ class MinecraftPolicy(nn.Module):
         cfg = self.cfg
         H, W = cfg.img_shape[0], cfg.img_shape[1]
         x, mr = None, None
+        if prep.conv3d is not None:  # IDM: img is (b, T, H, W, 3), whole sequences (the temporal conv needs its neighbours)
+            x, mr = ops.conv3d_t5(img, prep.conv3d[0], prep.conv3d[1], cfg.conv3d_out)
+            self._tap("conv3d", x)
         for i, c in enumerate(cfg.chans):
             st = prep.stacks[i]
             if i == 0 and "fc_w" in st:
@@ -387,21 +410,27 @@ class MinecraftPolicy(nn.Module):
         if img.dtype != torch.uint8:
             raise TypeError("ob['img'] must be uint8 (B,T,H,W,3) as in the reference (lib/policy.py:39-45)")
         B, t = img.shape[:2]
-        assert tuple(img.shape[2:]) == cfg.img_shape, f"img shape {tuple(img.shape[2:])} != {cfg.img_shape}"
+        frame_shape = (cfg.img_shape[0], cfg.img_shape[1], 3)
+        assert tuple(img.shape[2:]) == frame_shape, f"img shape {tuple(img.shape[2:])} != {frame_shape}"
         assert len(state_in) == cfg.n_layers, \
             f"Length of state {len(state_in)} did not match length of blocks {cfg.n_layers}"  # lib/util.py:117-119
         prep = self.prepared()
         N = B * t
-        frames = img.reshape(N, *cfg.img_shape).contiguous()
+        frames = img.reshape(N, *frame_shape).contiguous()
         first_u8 = first.to(device=img.device, dtype=torch.bool).contiguous().view(torch.uint8)
         Hf, Wf = cfg.final_hw
         C2 = cfg.chans[-1]
         # ---- ImpalaCNN in frame chunks (bounds the activation workspace), then ONE dense GEMM over all frames
         cnn_out = torch.empty((N, Hf + 1, Wf + 1, C2), dtype=BF16, device=img.device)
         mrs = []
-        for f0 in range(0, N, self.cnn_chunk_frames):
-            F_ = min(self.cnn_chunk_frames, N - f0)
-            _, mr = self._cnn_chunk(frames[f0:f0 + F_], prep, cnn_out[f0:f0 + F_])
+        if cfg.conv3d_out is None:
+            step = self.cnn_chunk_frames
+        else:  # chunks of whole sequences; the IDM's 128-channel full-resolution stage is ~13 MiB/frame
+            step = max(1, self.idm_chunk_frames // t) * t
+        for f0 in range(0, N, step):
+            F_ = min(step, N - f0)
+            chunk = frames[f0:f0 + F_] if cfg.conv3d_out is None else frames[f0:f0 + F_].view(F_ // t, t, *frame_shape)
+            _, mr = self._cnn_chunk(chunk, prep, cnn_out[f0:f0 + F_])
             mrs.append(mr)
         mr_c = mrs[0] if len(mrs) == 1 else torch.cat(mrs, 0)
         Kd = (Hf + 1) * (Wf + 1) * C2  # ZP rows flattened; the zero row / column meets zero weight columns
@@ -430,25 +459,40 @@ class MinecraftPolicy(nn.Module):
         return (latent, latent), state_out
 
 
+class InverseActionNet(MinecraftPolicy):
+    """lib/policy.py:342-403: conv3d pre-stage -> ImpalaCNN (first conv normalised) -> unmasked transformer ->
+    relu -> final_ln.  `lastlayer` keeps its parameters (state_dict schema) but its output is discarded by the reference
+    (lib/policy.py:390-391), so it is not computed."""
+
+    def __init__(self, hidsize=512, conv3d_params=None, **MCPoliy_kwargs):
+        super().__init__(hidsize=hidsize, conv3d_params=conv3d_params, **MCPoliy_kwargs)
+
+    def forward(self, ob, state_in, context):
+        """lib/policy.py:374-392 -> ((pi_latent, None), state_out)."""
+        first = context["first"]
+        _, latent, state_out = self._forward_impl(ob["img"], first, state_in, use_lastlayer=False)
+        return (latent, None), state_out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # heads + MinecraftAgentPolicy
 # ---------------------------------------------------------------------------------------------------------------
-class MinecraftAgentPolicy(nn.Module):
-    """lib/policy.py:227-339."""
+class _PolicyBase(nn.Module):
+    """Shared head plumbing of MinecraftAgentPolicy and InverseActionPolicy (lib/action_head.py:136-260)."""
 
-    def __init__(self, action_space, policy_kwargs, pi_head_kwargs):
-        super().__init__()
-        self.net = MinecraftPolicy(**policy_kwargs)
+    has_value_head = True
+
+    def _init_heads(self, action_space, pi_head_kwargs):
         self.action_space = action_space
-        self.temperature = float(pi_head_kwargs.get("temperature", 1.0))
+        self.temperature = float((pi_head_kwargs or {}).get("temperature", 1.0))
         h = self.net.output_latent_size()
-        # value head: lib/scaled_mse_head.py:24 + lib/normalize_ewma.py:18-20
-        w, b = _default_linear(1, h)
-        _set(self, "value_head.linear.weight", w)
-        _set(self, "value_head.linear.bias", b)
-        _set(self, "value_head.normalizer.running_mean", torch.zeros(1), requires_grad=False)
-        _set(self, "value_head.normalizer.running_mean_sq", torch.zeros(1), requires_grad=False)
-        _set(self, "value_head.normalizer.debiasing_term", torch.tensor(0.0), requires_grad=False)
+        if self.has_value_head:  # lib/scaled_mse_head.py:24 + lib/normalize_ewma.py:18-20
+            w, b = _default_linear(1, h)
+            _set(self, "value_head.linear.weight", w)
+            _set(self, "value_head.linear.bias", b)
+            _set(self, "value_head.normalizer.running_mean", torch.zeros(1), requires_grad=False)
+            _set(self, "value_head.normalizer.running_mean_sq", torch.zeros(1), requires_grad=False)
+            _set(self, "value_head.normalizer.debiasing_term", torch.tensor(0.0), requires_grad=False)
         # pi head: lib/action_head.py:263-275 -> one CategoricalActionHead per Discrete TensorType, in dict order
         self.head_specs = OrderedDict()
         for name, space in action_space.items():
@@ -464,7 +508,6 @@ class MinecraftAgentPolicy(nn.Module):
         self._hprep = None
         self._hprep_fp = None
 
-    # -- API ------------------------------------------------------------------------------------------------
     def initial_state(self, batch_size: int):
         return self.net.initial_state(batch_size)
 
@@ -480,8 +523,9 @@ class MinecraftAgentPolicy(nn.Module):
                     bs.append(lin.bias.detach())
                     cols[name] = (c0, lin.weight.shape[0])
                     c0 += lin.weight.shape[0]
-                self._hprep = dict(pi=_fold_linear(torch.cat(ws, 0), bias=torch.cat(bs, 0)), cols=cols, ntot=c0,
-                                   v=_fold_linear(self.value_head.linear.weight.detach(), bias=self.value_head.linear.bias.detach()))
+                self._hprep = dict(pi=_fold_linear(torch.cat(ws, 0), bias=torch.cat(bs, 0)), cols=cols, ntot=c0)
+                if self.has_value_head:
+                    self._hprep["v"] = _fold_linear(self.value_head.linear.weight.detach(), bias=self.value_head.linear.bias.detach())
             self._hprep_fp = fp
         return self._hprep
 
@@ -505,21 +549,10 @@ class MinecraftAgentPolicy(nn.Module):
             else:  # several sub-actions per head (IDM): softmax over each group of n columns
                 lp = torch.cat([ops.log_softmax(raw, c0 + i * n, n) for i in range(cnt)], dim=1)
             pd[name] = lp.view(B, t, *shape, n)
+        if not self.has_value_head:
+            return pd, None
         vpred, _ = self.net._linear(lat_bf16, hp["v"], 1, out_dtype=F32)
         return pd, vpred.view(B, t, 1)
-
-    def forward(self, obs, first: torch.Tensor, state_in):
-        """lib/policy.py:252-269 -> ((pi_logits, vpred, None), state_out)."""
-        if isinstance(obs, dict):
-            obs = obs.copy()
-            mask = obs.pop("mask", None)
-        else:
-            mask = None
-        lat_bf16, _, state_out = self.net._forward_impl(obs["img"], first, state_in)
-        B, t = obs["img"].shape[:2]
-        pi_logits, vpred = self._heads(lat_bf16, B, t, mask)
-        return (pi_logits, vpred, None), state_out
-
     # -- distribution helpers (lib/action_head.py:176-220, 250-260) ---------------------------------------------
     def sample(self, pd, deterministic: bool = False):
         """DictActionHead.sample: per head in dict order; `torch.rand_like` supplies the uniforms so the Philox stream
@@ -540,6 +573,28 @@ class MinecraftAgentPolicy(nn.Module):
                 lp = lp.sum(dim=-1)
             tot = lp if tot is None else tot + lp
         return tot
+
+
+
+class MinecraftAgentPolicy(_PolicyBase):
+    """lib/policy.py:227-339."""
+
+    def __init__(self, action_space, policy_kwargs, pi_head_kwargs):
+        super().__init__()
+        self.net = MinecraftPolicy(**policy_kwargs)
+        self._init_heads(action_space, pi_head_kwargs)
+
+    def forward(self, obs, first: torch.Tensor, state_in):
+        """lib/policy.py:252-269 -> ((pi_logits, vpred, None), state_out)."""
+        if isinstance(obs, dict):
+            obs = obs.copy()
+            mask = obs.pop("mask", None)
+        else:
+            mask = None
+        lat_bf16, _, state_out = self.net._forward_impl(obs["img"], first, state_in)
+        B, t = obs["img"].shape[:2]
+        pi_logits, vpred = self._heads(lat_bf16, B, t, mask)
+        return (pi_logits, vpred, None), state_out
 
     def denormalize(self, v):
         """lib/normalize_ewma.py:31-35,57-60 (a 3-scalar affine map; host-side glue)."""
@@ -598,3 +653,35 @@ class MinecraftAgentPolicy(nn.Module):
         first = first.unsqueeze(1)
         (pd, vpred, _), state_out = self(obs=obs, first=first, state_in=state_in)
         return self.denormalize(vpred)[:, 0]
+
+
+class InverseActionPolicy(_PolicyBase):
+    """lib/policy.py:406-467 (the IDM): InverseActionNet + factored categorical heads, no value head."""
+
+    has_value_head = False
+
+    def __init__(self, action_space, pi_head_kwargs=None, idm_net_kwargs=None):
+        super().__init__()
+        self.net = InverseActionNet(**idm_net_kwargs)
+        self._init_heads(action_space, pi_head_kwargs)
+
+    def forward(self, obs, first: torch.Tensor, state_in, **kwargs):
+        """lib/policy.py:432-446 -> ((pi_logits, None, None), state_out)."""
+        if isinstance(obs, dict):
+            obs = obs.copy()
+            mask = obs.pop("mask", None)
+        else:
+            mask = None
+        lat_bf16, _, state_out = self.net._forward_impl(obs["img"], first, state_in, use_lastlayer=False)
+        B, t = obs["img"].shape[:2]
+        pi_logits, _ = self._heads(lat_bf16, B, t, mask)
+        return (pi_logits, None, None), state_out
+
+    @torch.no_grad()
+    def predict(self, obs, deterministic: bool = True, **kwargs):
+        """lib/policy.py:448-464."""
+        (pd, _, _), state_out = self(obs=obs, **kwargs)
+        ac = self.sample(pd, deterministic=deterministic)
+        log_prob = self.logprob(ac, pd)
+        assert not torch.isnan(log_prob).any()
+        return ac, state_out, {"log_prob": log_prob, "pd": pd}
