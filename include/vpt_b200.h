@@ -115,6 +115,9 @@ int vpt_conv3x3_zp(const vpt_conv_zp_args* args, void* stream);
 /* SM pairs cooperating on 256-row tiles with tcgen05.mma.cta_group::2 (each CTA stages half of the weight tile):
  * 0 = never, 1 = auto (default: pairs when Cout > 128, where they measure +11-13 %), 2 = always.  Tuning / A-B knob. */
 int vpt_set_conv_pair_mode(int32_t on);
+/* 1 (default): Cout == 128 layers run the operand-swapped kernel (channels as UMMA M, 256 pixels as N; see
+ * csrc/conv_zp_t.cuh); 0: the regular orientation.  Changes vpt_conv_zp_stat_parts(128).  Tuning / A-B knob. */
+int vpt_set_conv_swap_mode(int32_t on);
 int vpt_conv_zp_stat_parts(int32_t Cout);
 
 /* ----------------------------------------------------------------------------------------------------------

@@ -121,8 +121,10 @@ def test_conv3x3_zp(H, W, Cin, Cout, F_):
     S1, S2 = torch.randn(9, Cout, generator=g), torch.randn(9, Cout, generator=g)
     res = E.to_zp(_rand((F_, H, W, Cout), g))
     try:
-        for pair in (0, 2):  # one CTA per tile / SM pairs with tcgen05.mma.cta_group::2
+        # pair: one CTA per tile / SM pairs with tcgen05.mma.cta_group::2; swap: operand-swapped kernel for Cout == 128
+        for pair, swap in ((0, 0), (2, 0), (0, 1)) if Cout == 128 else ((0, 0), (2, 0)):
             nat.lib().vpt_set_conv_pair_mode(pair)
+            nat.lib().vpt_set_conv_swap_mode(swap)
             for residual in (None, res):
                 got, gmr = ops.conv3x3_zp(x.to(DEV), Wb.to(DEV), H, W, mr=mr.to(DEV), S1=S1.to(DEV), S2=S2.to(DEV), relu=1,
                                           residual=None if residual is None else residual.to(DEV))
@@ -130,10 +132,11 @@ def test_conv3x3_zp(H, W, Cin, Cout, F_):
                 ref, rmr = E.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, residual=residual)
                 gc = got.cpu()
                 assert (gc[:, -1] == 0).all() and (gc[:, :, -1] == 0).all(), "ZP zero row/column not maintained by the conv epilogue"
-                _close(f"conv3x3_zp pair={pair} {F_}x{H}x{W} {Cin}->{Cout} res={residual is not None}", got, ref)
-                _close(f"conv3x3_zp stats pair={pair}", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
+                _close(f"conv3x3_zp pair={pair} swap={swap} {F_}x{H}x{W} {Cin}->{Cout} res={residual is not None}", got, ref)
+                _close(f"conv3x3_zp stats pair={pair} swap={swap}", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
     finally:
         nat.lib().vpt_set_conv_pair_mode(1)
+        nat.lib().vpt_set_conv_swap_mode(1)
 
 
 def test_zp_pool_norm():

@@ -7,7 +7,7 @@ from video_pre_training_b200 import _native as nat, ops
 l = nat.lib()
 g = torch.Generator().manual_seed(0)
 shapes = [(64, 128, 128, 2048), (64, 128, 256, 1024), (32, 256, 256, 2048), (16, 256, 256, 4096)]
-variants = [(0, 0), (2, 0)]  # (pair mode, -)
+variants = [(0, 0), (2, 0), (0, 1)]  # (pair mode, swap mode)
 for (HW, Cin, N, F_) in shapes:
     x = torch.zeros(F_, HW + 1, HW + 1, Cin, dtype=torch.bfloat16, device="cuda")
     x[:, :HW, :HW] = torch.randn(F_, HW, HW, Cin, device="cuda").to(torch.bfloat16)
@@ -17,7 +17,7 @@ for (HW, Cin, N, F_) in shapes:
     fl = 2.0 * F_ * HW * HW * N * 9 * Cin
     ref = None
     for (nsplit, korder) in variants:
-        l.vpt_set_conv_pair_mode(nsplit)
+        l.vpt_set_conv_pair_mode(nsplit); l.vpt_set_conv_swap_mode(korder)
         for _ in range(2):
             out, _ = ops.conv3x3_zp(x, Wb, HW, HW, mr=mr, S1=S1, S2=S2, relu=1, want_stats=False)
         torch.cuda.synchronize()
@@ -30,5 +30,5 @@ for (HW, Cin, N, F_) in shapes:
         nat.device_check()
         if ref is None: ref = out.float()
         err = ((out.float() - ref).norm() / ref.norm()).item()
-        print(f"HW={HW} Cin={Cin} N={N} F={F_}: pair={nsplit}: {ms:7.3f} ms  {fl/ms/1e9:7.0f} TFLOP/s (algorithmic)  diff vs first {err:.1e}")
-l.vpt_set_conv_pair_mode(1)
+        print(f"HW={HW} Cin={Cin} N={N} F={F_}: pair={nsplit} swap={korder}: {ms:7.3f} ms  {fl/ms/1e9:7.0f} TFLOP/s (algorithmic)  diff vs first {err:.1e}")
+l.vpt_set_conv_pair_mode(1); l.vpt_set_conv_swap_mode(1)

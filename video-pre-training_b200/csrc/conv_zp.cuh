@@ -359,6 +359,11 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 }  // namespace vpt
 
+namespace vpt {
+extern int g_cz_swap_enabled();
+int launch_conv_zp_t_fwd(const vpt_conv_zp_args* a, void* stream);
+}  // namespace vpt
+
 extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     using namespace vpt;
     VPT_CHECK(a && a->x && a->w && a->out, "vpt_conv3x3_zp: null operand");
@@ -367,6 +372,7 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
               "vpt_conv3x3_zp: need F>0, H,W>=2, Cin %% 64 == 0, Cout %% 16 == 0 (F=%d H=%d W=%d Cin=%d Cout=%d)", a->F, H, W, C, N);
     VPT_CHECK(W + 1 <= 255, "vpt_conv3x3_zp: W=%d too wide for one shared-memory span", W);
     VPT_CHECK(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->w & 15) == 0 && ((uintptr_t)a->out & 15) == 0, "vpt_conv3x3_zp: pointers must be 16-byte aligned");
+    if (N == 128 && g_cz_swap_enabled()) return launch_conv_zp_t_fwd(a, stream);  // operand-swapped kernel (conv_zp_t.cuh)
     ConvZpParams p;
     memset(&p, 0, sizeof(p));
     p.H = H; p.W = W; p.Wp = W + 1; p.FS = (H + 1) * (W + 1);
@@ -466,6 +472,7 @@ extern "C" int vpt_set_conv_pair_mode(int32_t on) {
 }
 
 extern "C" int vpt_conv_zp_stat_parts(int32_t Cout) {
+    if (Cout == 128 && vpt::g_cz_swap_enabled()) return 4;  // swapped kernel: one partial per 32-channel quarter
     int bn, nt;
     vpt::choose_block_n(Cout, &bn, &nt);
     return nt * 2;

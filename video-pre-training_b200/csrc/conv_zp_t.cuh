@@ -1,0 +1,321 @@
+// Operand-swapped variant of conv3x3_zp for Cout == 128: D^T[channel][pixel] = W[channel][k] * X[pixel][k]^T.
+//
+// Why: single-CTA SS-mode UMMA time is set by the operand rows it fetches from shared memory, ~(M_rows + N_rows)/2 + 12
+// cycles per instruction.  With pixels as M (128) and 128 output channels as N that is 140 cycles for
+// 128x128x16 MACs (46 % of the tensor pipe); with the 128 channels as M and 256 PIXELS as N it is 204 cycles for twice the
+// work (63 %).  The price is a transposed accumulator: TMEM lane = output channel, TMEM column = pixel, so each epilogue
+// thread owns one channel and walks over pixels; global accesses stay coalesced because the 32 lanes of a warp are 32
+// consecutive channels of one pixel (64 contiguous bytes), and the per-pixel statistics are produced with a butterfly
+// transpose-reduce across the warp.
+//
+//   warp 0: activation-span TMA producer   warp 1: MMA issuer   warp 2: weight-tile TMA producer   warps 3..10: epilogue
+#pragma once
+#include "conv_zp.cuh"
+
+namespace vpt {
+
+constexpr int kCtPix = 256;  // pixel rows (ZP linear index) per tile = UMMA N
+
+struct ConvZpTParams {
+    long long Q;
+    int H, W, Wp, FS;
+    int cin, cin_blocks;
+    int a_box_rows, a_boxes, a_stage_bytes, b_stages;
+    long long num_tiles;
+    const float* mr;
+    const float* S1;  // [9][128]
+    const float* S2;  // [9][128]
+    int relu;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    float* stat_part;  // [Q][4] float2 (one slot per 32-channel quarter) or null
+};
+
+// lane L ends up with the sum over the warp's 32 lanes of x[L]  (31 shuffles)
+__device__ __forceinline__ float transpose_reduce32(float (&x)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? x[i] : x[i + s];
+            const float keep = up ? x[i + s] : x[i];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return x[0];
+}
+
+__global__ void __launch_bounds__(kCzThreads, 1)
+conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvZpTParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    constexpr uint32_t w_stage_bytes = 128 * kBlockK * 2;  // [128 channels][64 k]
+    uint8_t* smem_x = smem;                                 // 2 activation-span stages
+    uint8_t* smem_w = smem + 2 * (size_t)p.a_stage_bytes;   // weight tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + (size_t)p.b_stages * w_stage_bytes);
+    uint64_t* x_full = bars;
+    uint64_t* x_empty = bars + 2;
+    uint64_t* w_full = bars + 4;
+    uint64_t* w_empty = bars + 4 + kCzMaxBStages;
+    uint64_t* tmem_full_bar = bars + 4 + 2 * kCzMaxBStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* s_tab = reinterpret_cast<float*>(tmem_ptr_smem + 4);       // [2][9][128]: S1, S2
+    float4* s_pix = reinterpret_cast<float4*>(s_tab + 2 * 9 * 128);   // [2 buffers][256]: (ga, gb, cls, -)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&x_full[i], 1);
+            mbar_init(&x_empty[i], 1);
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+        }
+        for (int i = 0; i < p.b_stages; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < 9 * 128; i += blockDim.x) {
+        s_tab[i] = p.S1 ? __ldg(p.S1 + i) : 0.f;
+        s_tab[9 * 128 + i] = p.S2 ? __ldg(p.S2 + i) : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int halo = p.Wp + 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= activation-span producer =================
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+                const long long span0 = tile * kCtPix - halo;
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    if (!(ok = mbar_wait(&x_empty[stage], phase ^ 1u, 0x510u))) break;
+                    mbar_expect_tx(&x_full[stage], (uint32_t)p.a_stage_bytes);
+                    uint8_t* sx = smem_x + (size_t)stage * p.a_stage_bytes;
+                    for (int b = 0; b < p.a_boxes; ++b)
+                        tma_load_2d(sx + (size_t)b * p.a_box_rows * 128, &tmX, &x_full[stage], cb * kBlockK, (int)(span0 + (long long)b * p.a_box_rows));
+                    advance(stage, phase, 2);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ================= weight producer =================
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+                for (int cb = 0; cb < p.cin_blocks && ok; ++cb) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!(ok = mbar_wait(&w_empty[stage], phase ^ 1u, 0x520u))) break;
+                        mbar_expect_tx(&w_full[stage], w_stage_bytes);
+                        tma_load_2d(smem_w + (size_t)stage * w_stage_bytes, &tmW, &w_full[stage], tap * p.cin + cb * kBlockK, 0);
+                        advance(stage, phase, p.b_stages);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer: D[channel][pixel] += W_tile[channel][k] * X_span[pixel + shift][k] =================
+            const uint32_t idesc = umma_idesc_bf16(128, kCtPix);
+            int xstage = 0, wstage = 0;
+            uint32_t xphase = 0, wphase = 0;
+            int local = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
+                if (!(ok = mbar_wait(&tmem_empty_bar[as], accphase ^ 1u, 0x610u))) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStageCols);
+                for (int cb = 0; cb < p.cin_blocks && ok; ++cb) {
+                    if (!(ok = mbar_wait(&x_full[xstage], xphase, 0x710u))) break;
+                    tc_fence_after();
+                    const uint32_t x_base = smem_u32(smem_x + (size_t)xstage * p.a_stage_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!(ok = mbar_wait(&w_full[wstage], wphase, 0x720u))) break;
+                        tc_fence_after();
+                        const uint32_t w_addr = smem_u32(smem_w + (size_t)wstage * w_stage_bytes);
+                        const uint32_t x_addr = x_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(d_tmem, umma_desc_sw128(w_addr + k * 32), umma_desc_sw128(x_addr + k * 32), idesc, (uint32_t)((cb | tap | k) != 0));
+                        umma_commit(&w_empty[wstage]);
+                        advance(wstage, wphase, p.b_stages);
+                    }
+                    if (!ok) break;
+                    umma_commit(&x_empty[xstage]);
+                    advance(xstage, xphase, 2);
+                }
+                if (ok) umma_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else {
+        // ================= epilogue (warps 3..10): lane = channel, column = pixel =================
+        const int ew = warp - 3;
+        const int quarter = warp & 3;
+        const int chalf = ew >> 2;                        // pixel columns [chalf*128, +128)
+        const int ch = quarter * 32 + lane;               // output channel of this thread
+        const int et = ew * 32 + lane;                    // 0..255: index among the epilogue threads
+        int local = 0;
+        bool ok = true;
+        for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
+            const long long q0 = tile * kCtPix;
+            // per-pixel constants of this tile (one pixel per epilogue thread), double buffered by `as`
+            {
+                const long long q = q0 + et;
+                float4 info = make_float4(1.f, 0.f, -2.f, 0.f);  // cls -2: beyond the tensor
+                if (q < p.Q) {
+                    const long long f = q / p.FS;
+                    const int r = (int)(q - f * p.FS);
+                    const int y = r / p.Wp, x = r - y * p.Wp;
+                    if (y < p.H && x < p.W) {
+                        const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+                        const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+                        float ga = 1.f, gb = 0.f;
+                        if (p.mr) {
+                            const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
+                            ga = rstd;
+                            gb = rstd * mean;
+                        }
+                        info = make_float4(ga, gb, (float)(cy * 3 + cx), 0.f);
+                    } else {
+                        info.z = -1.f;  // zero row / column of the ZP layout
+                    }
+                }
+                s_pix[as * kCtPix + et] = info;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+
+            if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x810u))) break;
+            tc_fence_after();
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = chalf * 128 + c * 32;
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + col0), acc);
+                tmem_ld_wait();
+                float v[32], v2[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float4 info = s_pix[as * kCtPix + col0 + j];  // broadcast
+                    const int cls = (int)info.z;
+                    const long long q = q0 + col0 + j;
+                    float o = 0.f;
+                    if (cls >= 0) {
+                        const float s1 = s_tab[cls * 128 + ch], s2 = s_tab[9 * 128 + cls * 128 + ch];
+                        o = fmaf(info.x, __uint_as_float(acc[j]), fmaf(-info.y, s1, s2));
+                        if (p.relu == 1) o = fmaxf(o, 0.f);
+                        if (p.residual) o += __bfloat162float(p.residual[(size_t)q * 128 + ch]);
+                        if (p.relu == 2) o = fmaxf(o, 0.f);
+                    }
+                    const __nv_bfloat16 ob = __float2bfloat16_rn(o);
+                    if (cls >= -1) p.out[(size_t)q * 128 + ch] = ob;  // -1: the layout's zero row / column
+                    const float orr = __bfloat162float(ob);
+                    v[j] = orr;
+                    v2[j] = orr * orr;
+                }
+                if (p.stat_part) {
+                    const float s = transpose_reduce32(v, lane), ss = transpose_reduce32(v2, lane);
+                    const long long q = q0 + col0 + lane;
+                    if (q < p.Q) reinterpret_cast<float2*>(p.stat_part)[(size_t)q * 4 + quarter] = make_float2(s, ss);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int g_cz_swap = 1;
+
+// host launcher, called from vpt_conv3x3_zp when Cout == 128
+static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
+    const int H = a->H, W = a->W, C = a->Cin;
+    ConvZpTParams p;
+    memset(&p, 0, sizeof(p));
+    p.H = H; p.W = W; p.Wp = W + 1; p.FS = (H + 1) * (W + 1);
+    p.Q = (long long)a->F * p.FS;
+    p.cin = C; p.cin_blocks = C / 64;
+    p.num_tiles = (p.Q + kCtPix - 1) / kCtPix;
+    const int span = kCtPix + 2 * (p.Wp + 1);
+    p.a_boxes = (span + 255) / 256;
+    p.a_box_rows = ((span + p.a_boxes - 1) / p.a_boxes + 7) / 8 * 8;
+    VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
+    p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
+    const uint32_t w_stage_bytes = 128 * kBlockK * 2;
+    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 2 * 9 * 128 * 4 + 2 * kCtPix * 16 + 64;
+    const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - (long long)tail;
+    int bst = (int)(budget / w_stage_bytes);
+    if (bst > kCzMaxBStages) bst = kCzMaxBStages;
+    VPT_CHECK(bst >= 2, "vpt_conv3x3_zp: not enough shared memory for the weight pipeline (W=%d)", W);
+    p.b_stages = bst;
+    const size_t smem_bytes = 1024 + 2 * (size_t)p.a_stage_bytes + (size_t)bst * w_stage_bytes + tail;
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)p.Q};
+        cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.a_box_rows};
+        int r = make_tmap_bf16(&tmX, a->x, 2, dims, strides, box);
+        if (r) return r;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)9 * C, (cuuint64_t)128};
+        cuuint64_t strides[1] = {(cuuint64_t)9 * C * 2};
+        cuuint32_t box[2] = {64, 128};
+        int r = make_tmap_bf16(&tmW, a->w, 2, dims, strides, box);
+        if (r) return r;
+    }
+    p.mr = a->mr; p.S1 = a->mr ? a->S1 : nullptr; p.S2 = a->S2; p.relu = a->relu;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+    p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.stat_part = a->stat_part;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    long long grid = num_sms();
+    if (grid <= 0) grid = 148;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    conv3x3_zp_t_kernel<<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, p);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}
+
+int g_cz_swap_enabled() { return g_cz_swap; }
+int launch_conv_zp_t_fwd(const vpt_conv_zp_args* a, void* stream) { return launch_conv_zp_t(a, stream); }
+
+}  // namespace vpt
+
+extern "C" int vpt_set_conv_swap_mode(int32_t on) {
+    vpt::g_cz_swap = on ? 1 : 0;
+    return VPT_OK;
+}

@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
 
 #include "gemm_tc.cuh"
 #include "conv_zp.cuh"
+#include "conv_zp_t.cuh"
 #include "elementwise.cuh"
 #include "firstconv.cuh"
 #include "conv3d.cuh"
