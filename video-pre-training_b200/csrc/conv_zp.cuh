@@ -472,7 +472,7 @@ extern "C" int vpt_set_conv_pair_mode(int32_t on) {
 }
 
 extern "C" int vpt_conv_zp_stat_parts(int32_t Cout) {
-    if (Cout == 128 && vpt::g_cz_swap_enabled()) return 4;  // swapped kernel: one partial per 32-channel quarter
+    if (Cout == 128 && vpt::g_cz_swap_enabled()) return 4;  // swapped kernel: one partial per 32-channel part of a row
     int bn, nt;
     vpt::choose_block_n(Cout, &bn, &nt);
     return nt * 2;

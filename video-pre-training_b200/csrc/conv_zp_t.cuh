@@ -15,6 +15,7 @@
 namespace vpt {
 
 constexpr int kCtPix = 256;  // pixel rows (ZP linear index) per tile = UMMA N
+constexpr int kCtPitch = 132;  // fp32 elements per row of the transposed [pixel][channel] tile (528 B: conflict-free)
 
 struct ConvZpTParams {
     long long Q;
@@ -26,9 +27,10 @@ struct ConvZpTParams {
     const float* S1;  // [9][128]
     const float* S2;  // [9][128]
     int relu;
+    int dbg_skip_epilogue;
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
-    float* stat_part;  // [Q][4] float2 (one slot per 32-channel quarter) or null
+    float* stat_part;  // [Q][4] float2 (one slot per 32-channel part) or null
 };
 
 // lane L ends up with the sum over the warp's 32 lanes of x[L]  (31 shuffles)
@@ -62,8 +64,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint64_t* tmem_full_bar = bars + 4 + 2 * kCzMaxBStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    float* s_tab = reinterpret_cast<float*>(tmem_ptr_smem + 4);       // [2][9][128]: S1, S2
-    float4* s_pix = reinterpret_cast<float4*>(s_tab + 2 * 9 * 128);   // [2 buffers][256]: (ga, gb, cls, -)
+    float* s_tile = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [64 pixels][132] fp32: transposed quarter tile
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -86,10 +87,6 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (warp == 1) {
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
-    }
-    for (int i = threadIdx.x; i < 9 * 128; i += blockDim.x) {
-        s_tab[i] = p.S1 ? __ldg(p.S1 + i) : 0.f;
-        s_tab[9 * 128 + i] = p.S2 ? __ldg(p.S2 + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -169,80 +166,116 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
         }
     } else {
-        // ================= epilogue (warps 3..10): lane = channel, column = pixel =================
+        // ================= epilogue (warps 3..10) =================
+        // The accumulator is transposed (TMEM lane = output channel, column = pixel).  Measured (tools/conv_bench.py history):
+        // any per-element shared-memory LOOKUP in the channel-major phase costs more than the swap gains (the UMMA operand
+        // fetch already saturates the shared-memory pipe), while a plain transposing store is nearly free.  So:
+        //   phase A (thread = channel): TMEM -> fp32 -> transposed store into a [64 pixels][128 channels] fp32 tile
+        //           (32 lanes = 32 consecutive channels of one pixel = one 128-byte wavefront per instruction);
+        //   phase B (thread = pixel row x 32 channels): the regular epilogue -- fold with per-row constants and 16-byte table
+        //           loads, ReLU, residual, bf16 rounding, statistics, 16-byte global stores.
+        // Four 64-pixel quarters per tile keep the tile at 33 KB.
         const int ew = warp - 3;
         const int quarter = warp & 3;
-        const int chalf = ew >> 2;                        // pixel columns [chalf*128, +128)
-        const int ch = quarter * 32 + lane;               // output channel of this thread
-        const int et = ew * 32 + lane;                    // 0..255: index among the epilogue threads
+        const int cgrp = ew >> 2;                          // phase A: which 32 of the quarter's 64 pixel columns
+        const int ch = quarter * 32 + lane;                // phase A: output channel of this thread
+        const int et = ew * 32 + lane;                     // 0..255
+        const int brow = et & 63, bpart = et >> 6;         // phase B: pixel row of the quarter, 32-channel part
         int local = 0;
         bool ok = true;
         for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++local) {
             const int as = local & 1;
             const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
             const long long q0 = tile * kCtPix;
-            // per-pixel constants of this tile (one pixel per epilogue thread), double buffered by `as`
-            {
-                const long long q = q0 + et;
-                float4 info = make_float4(1.f, 0.f, -2.f, 0.f);  // cls -2: beyond the tensor
-                if (q < p.Q) {
-                    const long long f = q / p.FS;
-                    const int r = (int)(q - f * p.FS);
-                    const int y = r / p.Wp, x = r - y * p.Wp;
-                    if (y < p.H && x < p.W) {
-                        const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
-                        const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
-                        float ga = 1.f, gb = 0.f;
-                        if (p.mr) {
-                            const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
-                            ga = rstd;
-                            gb = rstd * mean;
-                        }
-                        info = make_float4(ga, gb, (float)(cy * 3 + cx), 0.f);
-                    } else {
-                        info.z = -1.f;  // zero row / column of the ZP layout
-                    }
-                }
-                s_pix[as * kCtPix + et] = info;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-
             if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x810u))) break;
             tc_fence_after();
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = chalf * 128 + c * 32;
-                uint32_t acc[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + col0), acc);
-                tmem_ld_wait();
-                float v[32], v2[32];
+            for (int h = 0; h < 4; ++h) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // previous phase B is done with the tile
+                if (p.dbg_skip_epilogue != 2) {
+                    uint32_t acc[32];
+                    const int pl0 = cgrp * 32;
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + h * 64 + pl0), acc);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float4 info = s_pix[as * kCtPix + col0 + j];  // broadcast
-                    const int cls = (int)info.z;
-                    const long long q = q0 + col0 + j;
-                    float o = 0.f;
-                    if (cls >= 0) {
-                        const float s1 = s_tab[cls * 128 + ch], s2 = s_tab[9 * 128 + cls * 128 + ch];
-                        o = fmaf(info.x, __uint_as_float(acc[j]), fmaf(-info.y, s1, s2));
-                        if (p.relu == 1) o = fmaxf(o, 0.f);
-                        if (p.residual) o += __bfloat162float(p.residual[(size_t)q * 128 + ch]);
-                        if (p.relu == 2) o = fmaxf(o, 0.f);
+                    for (int j = 0; j < 32; ++j) s_tile[(pl0 + j) * kCtPitch + ch] = __uint_as_float(acc[j]);
+                }
+                if (h == 3) {  // TMEM fully drained: release the accumulator stage to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // tile complete
+                if (p.dbg_skip_epilogue == 2) continue;
+                // ---- phase B: row q, channels [bpart*32, +32)
+                const long long q = q0 + h * 64 + brow;
+                if (q >= p.Q) continue;
+                const long long f = q / p.FS;
+                const int r = (int)(q - f * p.FS);
+                const int y = r / p.Wp, x = r - y * p.Wp;
+                __nv_bfloat16* op = p.out + (size_t)q * 128 + bpart * 32;
+                float st_s = 0.f, st_ss = 0.f;
+                if (y >= p.H || x >= p.W) {  // zero row / column of the ZP layout
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = make_uint4(0, 0, 0, 0);
+                } else {
+                    float ga = 1.f, gb = 0.f;
+                    if (p.mr) {
+                        const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
+                        ga = rstd;
+                        gb = rstd * mean;
                     }
-                    const __nv_bfloat16 ob = __float2bfloat16_rn(o);
-                    if (cls >= -1) p.out[(size_t)q * 128 + ch] = ob;  // -1: the layout's zero row / column
-                    const float orr = __bfloat162float(ob);
-                    v[j] = orr;
-                    v2[j] = orr * orr;
+                    const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+                    const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+                    const int cls = cy * 3 + cx;
+                    const float4* s1p = p.S1 ? reinterpret_cast<const float4*>(p.S1 + cls * 128 + bpart * 32) : nullptr;
+                    const float4* s2p = p.S2 ? reinterpret_cast<const float4*>(p.S2 + cls * 128 + bpart * 32) : nullptr;
+                    const float4* tp = reinterpret_cast<const float4*>(s_tile + brow * kCtPitch + bpart * 32);
+                    const uint4* rp = p.residual ? reinterpret_cast<const uint4*>(p.residual + (size_t)q * 128 + bpart * 32) : nullptr;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 a = tp[i];
+                        const float4 a1 = s1p ? __ldg(s1p + i) : make_float4(0, 0, 0, 0);
+                        const float4 a2 = s2p ? __ldg(s2p + i) : make_float4(0, 0, 0, 0);
+                        v[4 * i + 0] = fmaf(ga, a.x, fmaf(-gb, a1.x, a2.x));
+                        v[4 * i + 1] = fmaf(ga, a.y, fmaf(-gb, a1.y, a2.y));
+                        v[4 * i + 2] = fmaf(ga, a.z, fmaf(-gb, a1.z, a2.z));
+                        v[4 * i + 3] = fmaf(ga, a.w, fmaf(-gb, a1.w, a2.w));
+                    }
+                    if (p.relu == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (rp) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 rr = __ldg(rp + i);
+                            v[8 * i + 0] += bf16_lo(rr.x); v[8 * i + 1] += bf16_hi(rr.x);
+                            v[8 * i + 2] += bf16_lo(rr.y); v[8 * i + 3] += bf16_hi(rr.y);
+                            v[8 * i + 4] += bf16_lo(rr.z); v[8 * i + 5] += bf16_hi(rr.z);
+                            v[8 * i + 6] += bf16_lo(rr.w); v[8 * i + 7] += bf16_hi(rr.w);
+                        }
+                    }
+                    if (p.relu == 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                    if (p.stat_part) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+                            st_s += lo + hi;
+                            st_ss = fmaf(lo, lo, fmaf(hi, hi, st_ss));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
                 }
-                if (p.stat_part) {
-                    const float s = transpose_reduce32(v, lane), ss = transpose_reduce32(v2, lane);
-                    const long long q = q0 + col0 + lane;
-                    if (q < p.Q) reinterpret_cast<float2*>(p.stat_part)[(size_t)q * 4 + quarter] = make_float2(s, ss);
-                }
+                if (p.stat_part) reinterpret_cast<float2*>(p.stat_part)[(size_t)q * 4 + bpart] = make_float2(st_s, st_ss);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
         }
     }
 
@@ -271,7 +304,7 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
     p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
     const uint32_t w_stage_bytes = 128 * kBlockK * 2;
-    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 2 * 9 * 128 * 4 + 2 * kCtPix * 16 + 64;
+    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 64 * kCtPitch * 4 + 64;
     const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - (long long)tail;
     int bst = (int)(budget / w_stage_bytes);
     if (bst > kCzMaxBStages) bst = kCzMaxBStages;
@@ -297,6 +330,7 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     p.stat_part = a->stat_part;
+    p.dbg_skip_epilogue = (g_cz_swap == 2) ? 2 : 0;  // 2: no epilogue work (MMA-rate experiment)
     static bool attr_set = false;
     if (!attr_set) {
         VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -316,6 +350,6 @@ int launch_conv_zp_t_fwd(const vpt_conv_zp_args* a, void* stream) { return launc
 }  // namespace vpt
 
 extern "C" int vpt_set_conv_swap_mode(int32_t on) {
-    vpt::g_cz_swap = on ? 1 : 0;
+    vpt::g_cz_swap = on;  // 2 = debug: skip the epilogue arithmetic (MMA-rate experiment)
     return VPT_OK;
 }
