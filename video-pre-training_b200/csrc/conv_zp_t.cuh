@@ -190,6 +190,20 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x810u))) break;
             tc_fence_after();
             for (int h = 0; h < 4; ++h) {
+                // this thread's phase-B row: decode it and issue its residual loads NOW so that their (DRAM) latency
+                // overlaps the barrier and phase A instead of stalling all eight warps between the two barriers
+                const long long q = q0 + h * 64 + brow;
+                const bool q_ok = q < p.Q;
+                const long long f = q_ok ? q / p.FS : 0;
+                const int r = (int)(q - f * p.FS);
+                const int y = r / p.Wp, x = r - y * p.Wp;
+                const bool interior = q_ok && y < p.H && x < p.W;
+                uint4 rres[4];
+                if (interior && p.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)q * 128 + bpart * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rres[i] = __ldg(rp + i);
+                }
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // previous phase B is done with the tile
                 if (p.dbg_skip_epilogue != 2) {
                     uint32_t acc[32];
@@ -207,14 +221,10 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // tile complete
                 if (p.dbg_skip_epilogue == 2) continue;
                 // ---- phase B: row q, channels [bpart*32, +32)
-                const long long q = q0 + h * 64 + brow;
-                if (q >= p.Q) continue;
-                const long long f = q / p.FS;
-                const int r = (int)(q - f * p.FS);
-                const int y = r / p.Wp, x = r - y * p.Wp;
+                if (!q_ok) continue;
                 __nv_bfloat16* op = p.out + (size_t)q * 128 + bpart * 32;
                 float st_s = 0.f, st_ss = 0.f;
-                if (y >= p.H || x >= p.W) {  // zero row / column of the ZP layout
+                if (!interior) {  // zero row / column of the ZP layout
 #pragma unroll
                     for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = make_uint4(0, 0, 0, 0);
                 } else {
@@ -230,7 +240,6 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const float4* s1p = p.S1 ? reinterpret_cast<const float4*>(p.S1 + cls * 128 + bpart * 32) : nullptr;
                     const float4* s2p = p.S2 ? reinterpret_cast<const float4*>(p.S2 + cls * 128 + bpart * 32) : nullptr;
                     const float4* tp = reinterpret_cast<const float4*>(s_tile + brow * kCtPitch + bpart * 32);
-                    const uint4* rp = p.residual ? reinterpret_cast<const uint4*>(p.residual + (size_t)q * 128 + bpart * 32) : nullptr;
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -246,10 +255,10 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (rp) {
+                    if (p.residual) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const uint4 rr = __ldg(rp + i);
+                            const uint4 rr = rres[i];
                             v[8 * i + 0] += bf16_lo(rr.x); v[8 * i + 1] += bf16_hi(rr.x);
                             v[8 * i + 2] += bf16_lo(rr.y); v[8 * i + 3] += bf16_hi(rr.y);
                             v[8 * i + 4] += bf16_lo(rr.z); v[8 * i + 5] += bf16_hi(rr.z);
