@@ -189,21 +189,35 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const long long q0 = tile * kCtPix;
             if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x810u))) break;
             tc_fence_after();
-            for (int h = 0; h < 4; ++h) {
-                // this thread's phase-B row: decode it and issue its residual loads NOW so that their (DRAM) latency
-                // overlaps the barrier and phase A instead of stalling all eight warps between the two barriers
-                const long long q = q0 + h * 64 + brow;
-                const bool q_ok = q < p.Q;
-                const long long f = q_ok ? q / p.FS : 0;
-                const int r = (int)(q - f * p.FS);
-                const int y = r / p.Wp, x = r - y * p.Wp;
-                const bool interior = q_ok && y < p.H && x < p.W;
-                uint4 rres[4];
-                if (interior && p.residual) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)q * 128 + bpart * 32);
+            // phase-B row of this thread in quarter h: decode + residual loads are issued ONE QUARTER AHEAD so that their
+            // DRAM latency is covered by a whole phase A / phase B round instead of stalling all eight warps at a barrier
+            long long q_n = 0, f_n = 0;
+            int y_n = 0, x_n = 0;
+            bool qok_n = false, int_n = false;
+            uint4 rres_n[4];
+            auto prefetch_row = [&](int hh) {
+                q_n = q0 + hh * 64 + brow;
+                qok_n = q_n < p.Q;
+                f_n = qok_n ? q_n / p.FS : 0;
+                const int r = (int)(q_n - f_n * p.FS);
+                y_n = r / p.Wp;
+                x_n = r - y_n * p.Wp;
+                int_n = qok_n && y_n < p.H && x_n < p.W;
+                if (int_n && p.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)q_n * 128 + bpart * 32);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) rres[i] = __ldg(rp + i);
+                    for (int i = 0; i < 4; ++i) rres_n[i] = __ldg(rp + i);
                 }
+            };
+            prefetch_row(0);
+            for (int h = 0; h < 4; ++h) {
+                const long long q = q_n, f = f_n;
+                const int y = y_n, x = x_n;
+                const bool q_ok = qok_n, interior = int_n;
+                uint4 rres[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rres[i] = rres_n[i];
+                if (h < 3) prefetch_row(h + 1);
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // previous phase B is done with the tile
                 if (p.dbg_skip_epilogue != 2) {
                     uint32_t acc[32];
