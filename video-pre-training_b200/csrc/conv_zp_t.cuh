@@ -64,7 +64,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint64_t* tmem_full_bar = bars + 4 + 2 * kCzMaxBStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    float* s_tile = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [64 pixels][132] fp32: transposed quarter tile
+    float* s_tile0 = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // 2 x [64 pixels][132] fp32: transposed quarter tiles
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -218,7 +218,10 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rres[i] = rres_n[i];
                 if (h < 3) prefetch_row(h + 1);
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // previous phase B is done with the tile
+                // the transposed tile is double buffered (quarter h uses buffer h & 1): a warp that finishes phase B of quarter h
+                // goes straight on to phase A of quarter h + 1; the single barrier below orders A(h) -> B(h) and, because
+                // every warp reaches it only after its own B(h - 1), also B(h - 1) -> A(h + 1) on the same buffer.
+                float* s_tile = s_tile0 + (h & 1) * (64 * kCtPitch);
                 if (p.dbg_skip_epilogue != 2) {
                     uint32_t acc[32];
                     const int pl0 = cgrp * 32;
@@ -327,7 +330,7 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
     p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
     const uint32_t w_stage_bytes = 128 * kBlockK * 2;
-    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 64 * kCtPitch * 4 + 64;
+    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 2 * 64 * kCtPitch * 4 + 64;
     const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - (long long)tail;
     int bst = (int)(budget / w_stage_bytes);
     if (bst > kCzMaxBStages) bst = kCzMaxBStages;
