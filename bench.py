@@ -241,12 +241,17 @@ def run_ours(args):
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d2h = 0
+    from video_pre_training_b200.parallel import HostFramePipe
+    pipe = HostFramePipe(dev)
+    pipe.submit(host_img, host_first)
     for it in range(1 + args.steps):  # first iteration untimed (pinned-path warm-up)
         if it == 1:
             barrier()
             e2.record()
-        d_img = host_img.to(dev, non_blocking=True)
-        d_first = host_first.to(dev, non_blocking=True)
+            pipe.submit(host_img, host_first)  # every timed step uploads its own chunk inside the timed region
+        d_img, d_first = pipe.take()
+        if 1 <= it < args.steps:
+            pipe.submit(host_img, host_first)  # upload of the next step's frames overlaps this step's forward
         (pd, vpred, _), state2 = pol({"img": d_img}, d_first, state2)
         ac = pol.sample(pd)
         res = [ac["camera"].cpu(), ac["buttons"].cpu(), vpred.cpu()]  # device -> host read of the step's result (syncs)
@@ -256,7 +261,7 @@ def run_ours(args):
     ms2 = max_over_ranks(e2.elapsed_time(e3))
     e2e = {"value": world * frames_per_step * args.steps / (ms2 / 1000.0), "unit": "frames/s",
            "h2d_bytes_per_step": host_img.numel() + host_first.numel(), "d2h_bytes_per_step": d2h,
-           "call": "MinecraftAgentPolicy.forward(obs, first, state) + sample(); pinned host frames in, sampled actions + vpred out"}
+           "call": "HostFramePipe (pinned host frames -> device, double buffered) + MinecraftAgentPolicy.forward(obs, first, state) + sample(); sampled actions + vpred read back to the host every step"}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -26,3 +26,45 @@ def all_gather_rows(x: torch.Tensor, batch: int) -> torch.Tensor:
     outs = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf)
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
+
+
+class HostFramePipe:
+    """Double-buffered pinned-host -> device upload of (frames, first) chunks on a side stream, so that the upload of chunk
+    i+1 overlaps the forward of chunk i (the forward itself never waits on the host).  Usage:
+
+        pipe = HostFramePipe(device)
+        pipe.submit(host_img, host_first)            # starts the async copy of the first chunk
+        for ...:
+            img, first = pipe.take()                 # device tensors of the chunk submitted last; compute stream waits on the copy
+            pipe.submit(next_host_img, next_host_first)
+            out, state = policy({"img": img}, first, state)
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.events = [None, None]
+        self.cur = 0
+        self.pending = None
+
+    def submit(self, host_img: torch.Tensor, host_first: torch.Tensor):
+        i = self.cur
+        # the compute stream may still be reading slot i from two chunks ago: order the overwrite after it
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            img = host_img.to(self.device, non_blocking=True)
+            first = host_first.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.slots[i], self.events[i] = (img, first), ev
+        self.pending = i
+        self.cur ^= 1
+
+    def take(self):
+        i = self.pending
+        torch.cuda.current_stream(self.device).wait_event(self.events[i])
+        img, first = self.slots[i]
+        img.record_stream(torch.cuda.current_stream(self.device))
+        first.record_stream(torch.cuda.current_stream(self.device))
+        return img, first
