@@ -30,7 +30,7 @@ struct ConvZpTParams {
     int dbg_skip_epilogue;
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
-    float* stat_part;  // [Q][4] float2 (one slot per 32-channel part) or null
+    float* stat_part;  // [Q] float2 (complete row sums) or null
 };
 
 // lane L ends up with the sum over the warp's 32 lanes of x[L]  (31 shuffles)
@@ -65,6 +65,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     float* s_tile0 = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // 2 x [64 pixels][132] fp32: transposed quarter tiles
+    float4* s_info0 = reinterpret_cast<float4*>(s_tile0 + 2 * 64 * kCtPitch);  // 2 x [64]: per-row (ga, gb, cls)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -180,7 +181,6 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const int cgrp = ew >> 2;                          // phase A: which 32 of the quarter's 64 pixel columns
         const int ch = quarter * 32 + lane;                // phase A: output channel of this thread
         const int et = ew * 32 + lane;                     // 0..255
-        const int brow = et & 63, bpart = et >> 6;         // phase B: pixel row of the quarter, 32-channel part
         int local = 0;
         bool ok = true;
         for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++local) {
@@ -189,40 +189,54 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const long long q0 = tile * kCtPix;
             if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x810u))) break;
             tc_fence_after();
-            // phase-B row of this thread in quarter h: decode + residual loads are issued ONE QUARTER AHEAD so that their
-            // DRAM latency is covered by a whole phase A / phase B round instead of stalling all eight warps at a barrier
-            long long q_n = 0, f_n = 0;
-            int y_n = 0, x_n = 0;
-            bool qok_n = false, int_n = false;
+            // Phase-B work items: (row, 8-channel chunk).  A warp pass covers 2 rows x 16 chunks, lane = chunk*2 + row bit, so
+            // every global access of a pass touches 2 x 256 contiguous bytes (4 L1 wavefronts instead of the 32 of a
+            // thread-per-row mapping -- the L1/shared pipe is what the UMMA operand fetch competes for), and the fp32 tile
+            // reads are bank-conflict free.  Each warp does 4 passes per quarter; residual rows are prefetched a quarter ahead.
+            const int chunk = lane >> 1, c0 = chunk * 8;
             uint4 rres_n[4];
-            auto prefetch_row = [&](int hh) {
-                q_n = q0 + hh * 64 + brow;
-                qok_n = q_n < p.Q;
-                f_n = qok_n ? q_n / p.FS : 0;
-                const int r = (int)(q_n - f_n * p.FS);
-                y_n = r / p.Wp;
-                x_n = r - y_n * p.Wp;
-                int_n = qok_n && y_n < p.H && x_n < p.W;
-                if (int_n && p.residual) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)q_n * 128 + bpart * 32);
+            auto prefetch_res = [&](int hh) {
+                if (!p.residual) return;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) rres_n[i] = __ldg(rp + i);
+                for (int i = 0; i < 4; ++i) {
+                    const long long q = q0 + hh * 64 + 2 * (ew * 4 + i) + (lane & 1);
+                    if (q < p.Q) rres_n[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)q * 128 + c0));
                 }
             };
-            prefetch_row(0);
+            prefetch_res(0);
             for (int h = 0; h < 4; ++h) {
-                const long long q = q_n, f = f_n;
-                const int y = y_n, x = x_n;
-                const bool q_ok = qok_n, interior = int_n;
                 uint4 rres[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rres[i] = rres_n[i];
-                if (h < 3) prefetch_row(h + 1);
-                // the transposed tile is double buffered (quarter h uses buffer h & 1): a warp that finishes phase B of quarter h
-                // goes straight on to phase A of quarter h + 1; the single barrier below orders A(h) -> B(h) and, because
-                // every warp reaches it only after its own B(h - 1), also B(h - 1) -> A(h + 1) on the same buffer.
+                if (h < 3) prefetch_res(h + 1);
+                // the transposed tile and the row-info table are double buffered (quarter h uses buffer h & 1): the single
+                // barrier below orders A(h) -> B(h) and, because every warp reaches it only after its own B(h - 1), also
+                // B(h - 1) -> A(h + 1) on the same buffer.
                 float* s_tile = s_tile0 + (h & 1) * (64 * kCtPitch);
-                if (p.dbg_skip_epilogue != 2) {
+                float4* s_info = s_info0 + (h & 1) * 64;
+                if (et < 64) {  // per-row constants of this quarter: (ga, gb, cls); cls -1 = zero row/column, -2 = beyond the tensor
+                    const long long q = q0 + h * 64 + et;
+                    float4 info = make_float4(1.f, 0.f, -2.f, 0.f);
+                    if (q < p.Q) {
+                        const unsigned qq = (unsigned)q, f = qq / (unsigned)p.FS, r = qq - f * (unsigned)p.FS;
+                        const int y = (int)(r / (unsigned)p.Wp), x = (int)r - y * p.Wp;
+                        if (y < p.H && x < p.W) {
+                            const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+                            const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+                            float ga = 1.f, gb = 0.f;
+                            if (p.mr) {
+                                const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
+                                ga = rstd;
+                                gb = rstd * mean;
+                            }
+                            info = make_float4(ga, gb, (float)(cy * 3 + cx), 0.f);
+                        } else {
+                            info.z = -1.f;
+                        }
+                    }
+                    s_info[et] = info;
+                }
+                if (p.dbg_skip_epilogue != 2) {  // ---- phase A: TMEM -> transposed fp32 tile
                     uint32_t acc[32];
                     const int pl0 = cgrp * 32;
                     tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + h * 64 + pl0), acc);
@@ -235,72 +249,67 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // tile complete
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (p.dbg_skip_epilogue == 2) continue;
-                // ---- phase B: row q, channels [bpart*32, +32)
-                if (!q_ok) continue;
-                __nv_bfloat16* op = p.out + (size_t)q * 128 + bpart * 32;
-                float st_s = 0.f, st_ss = 0.f;
-                if (!interior) {  // zero row / column of the ZP layout
+                // ---- phase B
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = make_uint4(0, 0, 0, 0);
-                } else {
-                    float ga = 1.f, gb = 0.f;
-                    if (p.mr) {
-                        const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
-                        ga = rstd;
-                        gb = rstd * mean;
-                    }
-                    const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
-                    const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
-                    const int cls = cy * 3 + cx;
-                    const float4* s1p = p.S1 ? reinterpret_cast<const float4*>(p.S1 + cls * 128 + bpart * 32) : nullptr;
-                    const float4* s2p = p.S2 ? reinterpret_cast<const float4*>(p.S2 + cls * 128 + bpart * 32) : nullptr;
-                    const float4* tp = reinterpret_cast<const float4*>(s_tile + brow * kCtPitch + bpart * 32);
-                    float v[32];
+                for (int i = 0; i < 4; ++i) {
+                    const int prow = 2 * (ew * 4 + i) + (lane & 1);
+                    const long long q = q0 + h * 64 + prow;
+                    const float4 info = s_info[prow];
+                    const int cls = (int)info.z;
+                    float st_s = 0.f, st_ss = 0.f;
+                    if (cls >= -1) {
+                        uint4 o = make_uint4(0, 0, 0, 0);
+                        if (cls >= 0) {
+                            const float4 t0 = *reinterpret_cast<const float4*>(s_tile + prow * kCtPitch + c0);
+                            const float4 t1 = *reinterpret_cast<const float4*>(s_tile + prow * kCtPitch + c0 + 4);
+                            float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+                            if (p.S1) {
+                                a0 = __ldg(reinterpret_cast<const float4*>(p.S1 + cls * 128 + c0));
+                                a1 = __ldg(reinterpret_cast<const float4*>(p.S1 + cls * 128 + c0) + 1);
+                            }
+                            if (p.S2) {
+                                b0 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0));
+                                b1 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0) + 1);
+                            }
+                            float v[8] = {fmaf(info.x, t0.x, fmaf(-info.y, a0.x, b0.x)), fmaf(info.x, t0.y, fmaf(-info.y, a0.y, b0.y)),
+                                          fmaf(info.x, t0.z, fmaf(-info.y, a0.z, b0.z)), fmaf(info.x, t0.w, fmaf(-info.y, a0.w, b0.w)),
+                                          fmaf(info.x, t1.x, fmaf(-info.y, a1.x, b1.x)), fmaf(info.x, t1.y, fmaf(-info.y, a1.y, b1.y)),
+                                          fmaf(info.x, t1.z, fmaf(-info.y, a1.z, b1.z)), fmaf(info.x, t1.w, fmaf(-info.y, a1.w, b1.w))};
+                            if (p.relu == 1) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 a = tp[i];
-                        const float4 a1 = s1p ? __ldg(s1p + i) : make_float4(0, 0, 0, 0);
-                        const float4 a2 = s2p ? __ldg(s2p + i) : make_float4(0, 0, 0, 0);
-                        v[4 * i + 0] = fmaf(ga, a.x, fmaf(-gb, a1.x, a2.x));
-                        v[4 * i + 1] = fmaf(ga, a.y, fmaf(-gb, a1.y, a2.y));
-                        v[4 * i + 2] = fmaf(ga, a.z, fmaf(-gb, a1.z, a2.z));
-                        v[4 * i + 3] = fmaf(ga, a.w, fmaf(-gb, a1.w, a2.w));
-                    }
-                    if (p.relu == 1) {
+                                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                            }
+                            if (p.residual) {
+                                const uint4 rr = rres[i];
+                                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
+                                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                            }
+                            if (p.relu == 2) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                    if (p.residual) {
+                                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                            }
+                            o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 rr = rres[i];
-                            v[8 * i + 0] += bf16_lo(rr.x); v[8 * i + 1] += bf16_hi(rr.x);
-                            v[8 * i + 2] += bf16_lo(rr.y); v[8 * i + 3] += bf16_hi(rr.y);
-                            v[8 * i + 4] += bf16_lo(rr.z); v[8 * i + 5] += bf16_hi(rr.z);
-                            v[8 * i + 6] += bf16_lo(rr.w); v[8 * i + 7] += bf16_hi(rr.w);
+                            for (int k = 0; k < 4; ++k) {
+                                const float lo = bf16_lo(ow[k]), hi = bf16_hi(ow[k]);
+                                st_s += lo + hi;
+                                st_ss = fmaf(lo, lo, fmaf(hi, hi, st_ss));
+                            }
                         }
+                        *reinterpret_cast<uint4*>(p.out + (size_t)q * 128 + c0) = o;
                     }
-                    if (p.relu == 2) {
+                    if (p.stat_part) {  // row sums: reduce over the 16 chunk lanes of this row (lane bits 1..4)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-                    if (p.stat_part) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
-                            st_s += lo + hi;
-                            st_ss = fmaf(lo, lo, fmaf(hi, hi, st_ss));
+                        for (int m = 2; m <= 16; m <<= 1) {
+                            st_s += __shfl_xor_sync(0xffffffffu, st_s, m);
+                            st_ss += __shfl_xor_sync(0xffffffffu, st_ss, m);
                         }
+                        if (lane < 2 && cls >= -1) reinterpret_cast<float2*>(p.stat_part)[(size_t)q] = make_float2(st_s, st_ss);
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
                 }
-                if (p.stat_part) reinterpret_cast<float2*>(p.stat_part)[(size_t)q * 4 + bpart] = make_float2(st_s, st_ss);
             }
         }
     }
@@ -330,7 +339,7 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
     p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
     const uint32_t w_stage_bytes = 128 * kBlockK * 2;
-    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 2 * 64 * kCtPitch * 4 + 64;
+    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 2 * 64 * kCtPitch * 4 + 2 * 64 * 16 + 64;
     const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - (long long)tail;
     int bst = (int)(budget / w_stage_bytes);
     if (bst > kCzMaxBStages) bst = kCzMaxBStages;
