@@ -70,6 +70,16 @@ def test_fullsize_frames_2x_single_step():
     _check(res, "2x B=1 T=1")
 
 
+def test_fullsize_frames_3x_two_frames():
+    """3x width (chans 192/384/384, hidsize 3072, 24 heads): exercises the 192- and 2x192-wide conv tiles and C0 = 192."""
+    kw = vpt_b200.policy_kwargs("3x", n_recurrence_layers=1)
+    pol, sd, cfg = make_policy(kw, pert=False)
+    pol = pol.to(DEV)
+    res = run_chunks(pol, sd, cfg, B=1, chunks=[2], dev=DEV)
+    nat.device_check()
+    _check(res, "3x B=1 T=2")
+
+
 def test_act_sampling_bit_exact_given_logits():
     pol, sd, cfg = make_policy(small_kwargs())
     pol = pol.to(DEV)
