@@ -646,6 +646,11 @@ class MinecraftAgentPolicy(_PolicyBase):
         ac = {k: v[:, 0] for k, v in ac.items()}
         return ac, state_out, result
 
+    def make_graphed_act(self, batch_size: int):
+        """Rollout-latency path (agent.py:190-206, SURVEY f-1): returns a callable with the signature of `act` whose whole
+        step (forward + heads + sampling + log-prob + KV-memory roll) is ONE captured CUDA graph replay."""
+        return GraphedAct(self, batch_size)
+
     @torch.no_grad()
     def v(self, obs, first, state_in):
         """lib/policy.py:330-339."""
@@ -685,3 +690,65 @@ class InverseActionPolicy(_PolicyBase):
         log_prob = self.logprob(ac, pd)
         assert not torch.isnan(log_prob).any()
         return ac, state_out, {"log_prob": log_prob, "pd": pd}
+
+
+class GraphedAct:
+    """`MinecraftAgentPolicy.act` for a fixed batch size as a CUDA graph: ~170 kernel launches become one graph launch,
+    which is what bounds the B=1, T=1 rollout step (the arithmetic itself is ~0.1 ms of weight streaming at 2x width).
+
+    The recurrent state lives in static buffers owned by the graph; the state object returned by a call is a handle to
+    them (valid until the next call).  Passing any other state (e.g. `policy.initial_state(B)` after an episode reset)
+    copies it in.  Sampling uses torch's graph-safe Philox generator, i.e. the same `rand_like` draws as eager mode."""
+
+    def __init__(self, policy: "MinecraftAgentPolicy", batch_size: int):
+        self.policy = policy
+        cfg = policy.net.cfg
+        dev = policy.net.final_ln.weight.device
+        B, self.B = batch_size, batch_size
+        H, W = cfg.img_shape[0], cfg.img_shape[1]
+        self.img = torch.zeros((B, H, W, 3), dtype=torch.uint8, device=dev)
+        self.first = torch.zeros((B,), dtype=torch.bool, device=dev)
+        self.state = [(torch.zeros((B, 1, cfg.maxlen), dtype=torch.bool, device=dev),
+                       (torch.zeros((B, cfg.maxlen, cfg.hidsize), dtype=F32, device=dev),
+                        torch.zeros((B, cfg.maxlen, cfg.hidsize), dtype=F32, device=dev))) for _ in range(cfg.n_layers)]
+        policy.net.prepared()
+        policy._heads_prepared()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside capture (lazy function attributes, allocator pools)
+            for _ in range(2):
+                policy.act({"img": self.img}, self.first, self.state)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graphs = {}
+
+    def _capture(self, stochastic: bool):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ac, st, res = self.policy.act({"img": self.img}, self.first, self.state, stochastic=stochastic, return_pd=True)
+            for (m_in, (k_in, v_in)), (m_out, (k_out, v_out)) in zip(self.state, st):  # roll the state inside the graph
+                m_in.copy_(m_out)
+                k_in.copy_(k_out)
+                v_in.copy_(v_out)
+        self.graphs[stochastic] = (g, ac, res)
+        return self.graphs[stochastic]
+
+    @torch.no_grad()
+    def __call__(self, obs, first, state_in, stochastic: bool = True, taken_action=None, return_pd: bool = False):
+        if taken_action is not None:
+            raise NotImplementedError("GraphedAct: taken_action is only supported by the eager act()")
+        self.img.copy_(obs["img"])
+        self.first.copy_(first)
+        if state_in is not self.state:
+            for (m_in, (k_in, v_in)), (m, (k, v)) in zip(self.state, state_in):
+                if m is None:
+                    m_in.zero_()  # lib/masked_attention.py:75-76: None == all-False
+                else:
+                    m_in.copy_(m)
+                k_in.copy_(k)
+                v_in.copy_(v)
+        g, ac, res = self.graphs.get(stochastic) or self._capture(stochastic)
+        g.replay()
+        out = {"log_prob": res["log_prob"], "vpred": res["vpred"]}
+        if return_pd:
+            out["pd"] = res["pd"]
+        return ac, self.state, out
