@@ -639,7 +639,8 @@ class MinecraftAgentPolicy(_PolicyBase):
         else:
             ac = {k: v.unsqueeze(1) for k, v in taken_action.items()}
         log_prob = self.logprob(ac, pd)
-        assert not torch.isnan(log_prob).any()
+        if not torch.cuda.is_current_stream_capturing():  # the check synchronises; it cannot run inside a graph capture
+            assert not torch.isnan(log_prob).any()
         result = {"log_prob": log_prob[:, 0], "vpred": self.denormalize(vpred)[:, 0]}
         if return_pd:
             result["pd"] = {k: v[:, 0] for k, v in pd.items()}
