@@ -83,7 +83,8 @@ int vpt_gemm_bf16(const vpt_gemm_args* args, void* stream);
 /* Cluster size used when vpt_gemm_args.cluster == 0 (tuning knob; 1, 2 or 4; initial value 2). */
 int vpt_set_default_cluster(int32_t cluster);
 /* Hardware experiment hook used by tools/desc_experiment.py (A rows loaded `shift` rows early, UMMA descriptor start
- * advanced to compensate, base_offset field on/off).  Not for production use. */
+ * advanced to compensate, base_offset field on/off).  base_offset_mode = -1 (with shift 0) only disables the small-M
+ * weight-streaming kernel so that tests can force the tensor-core kernel.  Not for production use. */
 int vpt_debug_set(int32_t shift, int32_t base_offset_mode);
 /* Number of statistics partials per row (or per 32 rows) the GEMM emits for an N-column output. */
 int vpt_gemm_stat_parts(int32_t N);

@@ -76,6 +76,23 @@ def _gemm_case(M, N, K, g, *, conv=None, fold=False, relu=0, residual=None, out_
             _close(f"gemm stats cluster={cluster}", gst, rst, rtol=2e-3, atol=2e-3, l2=1e-3)
 
 
+def test_gemm_small_m_weight_streaming_path():
+    """M <= 8 rows take csrc/gemv_small.cuh (rollout path); same contract as the tensor-core kernel, incl. stats and row remap."""
+    g = torch.Generator().manual_seed(21)
+    for M in (1, 3, 8):
+        _gemm_case(M, 2048, 2048, g, bias=True, stats=1)
+        _gemm_case(M, 256, 73984, g, fold=True, relu=1, stats=1)
+        _gemm_case(M, 8762, 256, g, bias=True, out_f32=True, out_scale=0.5)
+        _gemm_case(M, 512, 256, g, bias=True, residual=BF16, relu=2, stats=1)
+    _gemm_case(4, 256, 256, g, seg=(2, 6, 4))
+    _gemm_case(1, 1, 2048, g, bias=True, out_f32=True)
+    try:  # and the tensor-core kernel on the same tiny shapes
+        nat.lib().vpt_debug_set(0, -1)
+        _gemm_case(3, 2048, 2048, g, bias=True, stats=1)
+    finally:
+        nat.lib().vpt_debug_set(0, 0)
+
+
 def test_gemm_linear_plain():
     g = torch.Generator().manual_seed(0)
     _gemm_case(128, 128, 64, g)

@@ -412,6 +412,7 @@ static inline void choose_block_n(int N, int* block_n, int* n_tiles) {
 }
 
 static int g_default_cluster = 1;
+static int g_small_m_enabled = 1;
 static int g_dbg_shift = 0, g_dbg_bo = 0;
 static int g_num_sms = 0;
 static int num_sms() {
@@ -434,6 +435,7 @@ extern "C" int vpt_set_default_cluster(int32_t cs) {
 extern "C" int vpt_debug_set(int32_t shift, int32_t bo) {
     vpt::g_dbg_shift = shift;
     vpt::g_dbg_bo = bo;
+    vpt::g_small_m_enabled = (shift == 0 && bo >= 0) ? 1 : 0;  // the descriptor experiment (and bo = -1) forces the tensor-core kernel
     return VPT_OK;
 }
 
@@ -441,6 +443,10 @@ extern "C" int vpt_gemm_stat_parts(int32_t N) {
     int bn, nt;
     vpt::choose_block_n(N, &bn, &nt);
     return nt * 2;
+}
+
+namespace vpt {
+int try_launch_gemv_small_fwd(const vpt_gemm_args* a, void* stream);
 }
 
 extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
@@ -451,6 +457,11 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     VPT_CHECK(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0, "vpt_gemm_bf16: A/B must be 16-byte aligned");
     VPT_CHECK(a->mr == nullptr || a->rows_per_group > 0, "vpt_gemm_bf16: rows_per_group must be > 0 with mr");
     VPT_CHECK(a->stat_part == nullptr || a->stat_mode == 1 || a->stat_mode == 2, "vpt_gemm_bf16: bad stat_mode %d", a->stat_mode);
+    VPT_CHECK(!(a->mr && !a->S1), "vpt_gemm_bf16: mr given without S1");
+    if (g_small_m_enabled) {  // rollout path: a handful of rows -> weight-streaming kernel (csrc/gemv_small.cuh)
+        const int r = try_launch_gemv_small_fwd(a, stream);
+        if (r <= 0) return r;
+    }
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = a->M; p.N = a->N; p.K = a->K;

@@ -1,0 +1,119 @@
+// Small-M linear layer (rollout path, B*T <= 8 tokens): out = epilogue(A[M][K] . W[N][K]^T) with the same epilogue contract as
+// vpt_gemm_bf16.  With one or a few rows the tensor pipe is irrelevant -- the layer is a read of the weight matrix at HBM
+// speed (2x model: 497 MB per step) -- and a 128-row tcgen05 tile would leave all but ceil(N/256) SMs idle.  So: one warp
+// per output column, lanes stride over K with 16-byte loads of W (streamed, read once) and of the A rows (L1/L2 resident),
+// fp32 FMA, warp-shuffle reduction, scalar epilogue; row statistics by a one-CTA-per-row follow-up in the same [M][P] layout.
+#pragma once
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+namespace vpt {
+
+constexpr int kGsMaxM = 8;
+constexpr int kGsThreads = 256;
+
+__global__ void __launch_bounds__(kGsThreads) gemv_small_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
+                                                                  const GemmParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = p.M, K8 = p.K >> 3;
+    for (int n = blockIdx.x * (kGsThreads / 32) + warp; n < p.N; n += gridDim.x * (kGsThreads / 32)) {
+        float acc[kGsMaxM];
+#pragma unroll
+        for (int m = 0; m < kGsMaxM; ++m) acc[m] = 0.f;
+        const uint4* wrow = reinterpret_cast<const uint4*>(W + (size_t)n * p.K);
+        for (int k = lane; k < K8; k += 32) {
+            const uint4 w = __ldg(wrow + k);
+            const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+            for (int m = 0; m < kGsMaxM; ++m) {
+                if (m < M) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(A + (size_t)m * p.K) + k);
+                    acc[m] = fmaf(bf16_lo(a.x), wf[0], acc[m]); acc[m] = fmaf(bf16_hi(a.x), wf[1], acc[m]);
+                    acc[m] = fmaf(bf16_lo(a.y), wf[2], acc[m]); acc[m] = fmaf(bf16_hi(a.y), wf[3], acc[m]);
+                    acc[m] = fmaf(bf16_lo(a.z), wf[4], acc[m]); acc[m] = fmaf(bf16_hi(a.z), wf[5], acc[m]);
+                    acc[m] = fmaf(bf16_lo(a.w), wf[6], acc[m]); acc[m] = fmaf(bf16_hi(a.w), wf[7], acc[m]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kGsMaxM; ++m) acc[m] = warp_sum(acc[m]);
+        if (lane == 0) {
+            const float s1 = p.S1 ? __ldg(p.S1 + n) : 0.f, s2 = p.S2 ? __ldg(p.S2 + n) : 0.f;
+#pragma unroll
+            for (int m = 0; m < kGsMaxM; ++m) {
+                if (m >= M) continue;
+                float ga = 1.f, gb = 0.f;
+                if (p.mr) {
+                    const int g = m / p.rows_per_group;
+                    const float mean = __ldg(p.mr + 2 * g), rstd = __ldg(p.mr + 2 * g + 1);
+                    ga = rstd;
+                    gb = rstd * mean;
+                }
+                float v = fmaf(ga, acc[m], fmaf(-gb, s1, s2));
+                if (p.relu == 1) v = fmaxf(v, 0.f);
+                if (p.residual) {
+                    v += p.residual_f32 ? reinterpret_cast<const float*>(p.residual)[(size_t)m * p.ld_res + n]
+                                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)m * p.ld_res + n]);
+                }
+                if (p.relu == 2) v = fmaxf(v, 0.f);
+                v *= p.out_scale;
+                long long orow = m;
+                if (p.seg_len > 0) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
+                if (p.out_f32) reinterpret_cast<float*>(p.out)[(size_t)orow * p.ld_out + n] = v;
+                else reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)orow * p.ld_out + n] = __float2bfloat16_rn(v);
+            }
+        }
+    }
+}
+
+// statistics partials of the rows just stored, in the [M][P] layout of the tensor-core kernel: slot 0 carries the whole
+// row's (sum, sumsq), the other slots are zero.  One CTA per row (M <= 8, N <= a few thousand): negligible.
+__global__ void __launch_bounds__(256) row_stats_small_kernel(const GemmParams p, int P) {
+    const int m = blockIdx.x;
+    long long orow = m;
+    if (p.seg_len > 0) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
+    float s = 0.f, ss = 0.f;
+    for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+        const float v = p.out_f32 ? reinterpret_cast<const float*>(p.out)[(size_t)orow * p.ld_out + n]
+                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.out)[(size_t)orow * p.ld_out + n]);
+        s += v;
+        ss = fmaf(v, v, ss);
+    }
+    const float2 r = block_sum2(s, ss);
+    float2* sp = reinterpret_cast<float2*>(p.stat_part) + (size_t)m * P;
+    if (threadIdx.x == 0) sp[0] = r;
+    for (int i = 1 + threadIdx.x; i < P; i += blockDim.x) sp[i] = make_float2(0.f, 0.f);
+}
+
+// returns VPT_OK after launching, or 1 if this shape is not handled here (caller falls through to the tensor-core kernel)
+static int try_launch_gemv_small(const vpt_gemm_args* a, void* stream) {
+    if (a->conv || a->M > kGsMaxM || (a->K & 7) != 0 || (a->stat_part && a->stat_mode != 1)) return 1;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.mr = a->mr; p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+    p.S1 = a->mr ? a->S1 : nullptr; p.S2 = a->S2;
+    p.relu = a->relu; p.out_scale = a->out_scale;
+    p.residual = a->residual; p.residual_f32 = a->residual_f32; p.ld_res = a->ld_res;
+    p.out = a->out; p.out_f32 = a->out_f32; p.ld_out = a->ld_out;
+    p.seg_len = a->seg_len; p.seg_stride = a->seg_stride; p.seg_off = a->seg_off;
+    p.stat_part = a->stat_part; p.stat_mode = a->stat_mode;
+    int bn, nt;
+    choose_block_n(a->N, &bn, &nt);
+    const int P = nt * 2;  // == vpt_gemm_stat_parts(N)
+    int grid = (a->N + kGsThreads / 32 - 1) / (kGsThreads / 32);
+    if (grid > 8 * 148) grid = 8 * 148;
+    gemv_small_kernel<<<grid, kGsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->A),
+                                                                     reinterpret_cast<const __nv_bfloat16*>(a->B), p);
+    VPT_LAUNCH_CHECK();
+    if (a->stat_part) {
+        row_stats_small_kernel<<<a->M, 256, 0, (cudaStream_t)stream>>>(p, P);
+        VPT_LAUNCH_CHECK();
+    }
+    return VPT_OK;
+}
+
+int try_launch_gemv_small_fwd(const vpt_gemm_args* a, void* stream) { return try_launch_gemv_small(a, stream); }
+
+}  // namespace vpt
