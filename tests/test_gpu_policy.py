@@ -158,3 +158,32 @@ def test_full_size_chunk_2x_rows_match_oracle_and_are_batch_independent():
                 e = rel_err(outs[ci][0][k][:1].cpu(), pd_o[k])
                 print(f"2x full-size chunk {ci} {k}: max rel err {e:.4g}, l2 {l2_err(outs[ci][0][k][:1].cpu(), pd_o[k]):.3g}")
                 assert e < RTOL_BF16, (ci, k, e)
+
+
+def test_graphed_act_matches_eager_and_logit_mask():
+    """Rollout path (SURVEY f-1): one CUDA-graph replay per step == the eager act(); plus the obs["mask"] side input."""
+    pol, sd, cfg = make_policy(small_kwargs())
+    pol = pol.to(DEV)
+    B = 2
+    step = pol.make_graphed_act(B)
+    g = torch.Generator().manual_seed(5)
+    st_a, st_b = pol.initial_state(B), pol.initial_state(B)
+    for i in range(10):  # > maxlen steps so that the KV memory rolls over
+        img = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+        first = torch.zeros(B, dtype=torch.bool, device=DEV)
+        if i == 6:
+            first[1] = True
+        ac_a, st_a, res_a = pol.act({"img": img}, first, st_a, stochastic=False, return_pd=True)
+        ac_b, st_b, res_b = step({"img": img}, first, st_b, stochastic=False, return_pd=True)
+        assert torch.equal(res_a["pd"]["buttons"], res_b["pd"]["buttons"]) and torch.equal(ac_a["camera"], ac_b["camera"]), i
+        assert torch.equal(st_a[0][1][0], st_b[0][1][0]) and torch.equal(st_a[1][0], st_b[1][0])
+    torch.manual_seed(9)
+    ac_s, _, _ = step({"img": img}, first, st_b, stochastic=True)
+    assert ac_s["buttons"].shape == (B, 1)
+    # logit mask: forbid every button combination but two -> all probability mass lands on them
+    mask = torch.zeros(B, 1, 1, 8641, dtype=torch.bool, device=DEV)
+    mask[..., [3, 77]] = True
+    (pd, _, _), _ = pol({"img": img[:, None], "mask": {"buttons": mask}}, first[:, None], pol.initial_state(B))
+    p = pd["buttons"].exp()
+    assert torch.allclose(p[..., [3, 77]].sum(-1), torch.ones(B, 1, 1, device=DEV), atol=1e-4)
+    nat.device_check()

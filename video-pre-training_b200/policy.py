@@ -541,9 +541,12 @@ class _PolicyBase(nn.Module):
         pd = OrderedDict()
         for name, (shape, n) in self.head_specs.items():
             c0, width = hp["cols"][name]
-            if mask is not None and mask.get(name) is not None:
-                raise NotImplementedError("vpt_b200: logit masks (obs['mask']) are not supported yet")
             cnt = width // n
+            if mask is not None and mask.get(name) is not None:
+                # lib/action_head.py:170-171: shaped_out[~mask] = LOG0 (-100) before the log-softmax.  Rare side input:
+                # applied as a masked fill on the raw (already temperature-scaled) logits.
+                view = raw[:, c0:c0 + width].view(B, t, *shape, n)
+                view.masked_fill_(~mask[name].to(device=raw.device, dtype=torch.bool).expand_as(view), -100.0)
             if cnt == 1:
                 lp = ops.log_softmax(raw, c0, n)
             else:  # several sub-actions per head (IDM): softmax over each group of n columns
