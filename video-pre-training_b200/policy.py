@@ -642,7 +642,7 @@ class MinecraftAgentPolicy(_PolicyBase):
         else:
             ac = {k: v.unsqueeze(1) for k, v in taken_action.items()}
         log_prob = self.logprob(ac, pd)
-        if not torch.cuda.is_current_stream_capturing():  # the check synchronises; it cannot run inside a graph capture
+        if not (log_prob.is_cuda and torch.cuda.is_current_stream_capturing()):  # the check synchronises: not inside a graph capture
             assert not torch.isnan(log_prob).any()
         result = {"log_prob": log_prob[:, 0], "vpred": self.denormalize(vpred)[:, 0]}
         if return_pd:
