@@ -203,6 +203,14 @@ int vpt_gumbel_argmax(const float* logits, const float* u, int64_t* idx, int64_t
 int vpt_gather_logprob(const float* logits, const int64_t* idx, float* lp, int64_t rows, int32_t n, int32_t accumulate,
                        void* stream);
 
+/* ----------------------------------------------------------------------------------------------------------
+ * BC step groundwork (behavioural_cloning.py:63-67,119-123): fused torch.optim.Adam(lr, weight_decay) step over ONE flat fp32
+ * bucket holding every parameter (gradients in a second flat bucket that data parallelism reduces with a single NCCL
+ * all-reduce; grad_scale = 1/world_size).  step counts from 1.  The backward kernels that fill `grads` are not built yet.
+ * -------------------------------------------------------------------------------------------------------- */
+int vpt_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -290,3 +290,25 @@ def test_heads_tail():
     lp = ops.gather_logprob(lg_d, got)
     assert torch.equal(lp.cpu(), lg.gather(-1, got.cpu().unsqueeze(-1)).squeeze(-1))
     nat.device_check()
+
+
+def test_fused_adam_matches_torch_optim():
+    """vpt_adam_step over a flat bucket vs torch.optim.Adam(lr, weight_decay) (behavioural_cloning.py:63-67), 5 steps."""
+    from video_pre_training_b200.parallel import FlatAdamDP
+    g = torch.Generator().manual_seed(31)
+    shapes = [(257, 33), (1001,), (64, 3, 3, 3), (7,)]
+    ref_params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    our_params = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_params]
+    ref = torch.optim.Adam(ref_params, lr=1.81e-4, weight_decay=0.039428)
+    ours = FlatAdamDP(our_params, lr=1.81e-4, weight_decay=0.039428)
+    for step in range(5):
+        grads = [torch.randn(s, generator=g) for s in shapes]
+        ours.zero_grad()
+        for p, q, gr in zip(ref_params, our_params, grads):
+            p.grad = gr.clone()
+            q.grad.copy_(gr.to(DEV))          # .grad aliases the flat gradient bucket
+        ref.step()
+        ours.step()
+    nat.device_check()
+    for p, q in zip(ref_params, our_params):
+        assert torch.allclose(q.detach().cpu(), p.detach(), rtol=1e-5, atol=1e-7), (q.detach().cpu() - p.detach()).abs().max()

@@ -1,5 +1,6 @@
 // libvpt_b200.so -- single translation unit (unity build) of the sm_100a kernels behind include/vpt_b200.h.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC vpt_b200.cu -o libvpt_b200.so
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -25,6 +26,7 @@ void set_error(const char* fmt, ...) {
 #include "conv3d.cuh"
 #include "attention.cuh"
 #include "heads.cuh"
+#include "adam.cuh"
 
 extern "C" const char* vpt_last_error(void) { return vpt::g_err; }
 extern "C" int vpt_abi_version(void) { return VPT_ABI_VERSION; }

@@ -68,3 +68,47 @@ class HostFramePipe:
         img.record_stream(torch.cuda.current_stream(self.device))
         first.record_stream(torch.cuda.current_stream(self.device))
         return img, first
+
+
+class FlatAdamDP:
+    """Data-parallel optimizer plumbing of the BC step (behavioural_cloning.py:63-67,119-123), independent of how the
+    gradients are produced: all parameters are re-pointed into ONE flat fp32 bucket, their `.grad`s into a second flat bucket,
+    so that a step is  one NCCL all-reduce (sum) over the gradient bucket  +  one fused Adam kernel (`vpt_adam_step`,
+    torch.optim.Adam semantics with L2 weight decay; 1/world_size folded into the kernel).  Parameters whose gradient is
+    None in the reference (value head under the BC loss) simply keep a zero gradient slice."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]  # 16-byte aligned slices
+        self.n = sum(sizes)
+        self.flat_p = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        off = 0
+        with torch.no_grad():
+            for p, sz in zip(self.params, sizes):
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view                                        # parameters now alias the flat bucket
+                p.grad = self.flat_g[off:off + p.numel()].view_as(p)  # and so do their gradients
+                off += sz
+        self.lr, self.betas, self.eps, self.weight_decay, self.t = lr, betas, eps, weight_decay, 0
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def step(self):
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)  # the single gradient all-reduce of the BC step
+        self.t += 1
+        if self.flat_p.is_cuda:
+            from . import _native as nat
+            nat.check(nat.lib().vpt_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
+                                              self.weight_decay, 1.0 / world, self.t, torch.cuda.current_stream().cuda_stream),
+                      "vpt_adam_step")
+        else:
+            raise RuntimeError("FlatAdamDP.step: the fused Adam kernel is CUDA only (no CPU fallback)")
