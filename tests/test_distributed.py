@@ -66,6 +66,42 @@ def test_batch_sharding_world2_gloo():
     assert all(r[2] for r in res) and all(r[3] == (5, 8, 1, 121) for r in res)
 
 
+def _adam_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vpt_b200  # noqa: F401
+    from video_pre_training_b200.parallel import FlatAdamDP
+
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    opt = FlatAdamDP(params, lr=1e-3)
+    ok_alias = params[0].data_ptr() == opt.flat_p.data_ptr() and params[1].grad.data_ptr() == opt.flat_g[16:].data_ptr()
+    opt.zero_grad()
+    params[0].grad.fill_(float(rank + 1))     # rank-dependent gradients written through the aliased views
+    params[1].grad.fill_(10.0 * (rank + 1))
+    w = opt.reduce_gradients()                # ONE all-reduce over the flat bucket
+    q.put((rank, w, ok_alias, params[0].grad.flatten()[0].item(), params[1].grad.flatten()[0].item()))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_single_allreduce_gloo():
+    """BC data-parallel plumbing: parameters / gradients alias flat buckets; one sum all-reduce."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_adam_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, w, ok_alias, g0, g1 in res:
+        assert w == 2 and ok_alias and g0 == 3.0 and g1 == 30.0
+
+
 def test_shard_range_covers_everything():
     from video_pre_training_b200 import parallel
 

@@ -99,10 +99,15 @@ class FlatAdamDP:
     def zero_grad(self):
         self.flat_g.zero_()
 
-    def step(self):
+    def reduce_gradients(self) -> int:
+        """The single gradient all-reduce (sum) of the BC step; returns the world size (the mean is folded into the Adam kernel)."""
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)  # the single gradient all-reduce of the BC step
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        return world
+
+    def step(self):
+        world = self.reduce_gradients()
         self.t += 1
         if self.flat_p.is_cuda:
             from . import _native as nat
