@@ -103,6 +103,7 @@ def test_flat_gradient_bucket_single_allreduce_gloo():
 
 
 def test_shard_range_covers_everything():
+    import vpt_b200  # noqa: F401  (registers the hyphenated package directory as video_pre_training_b200)
     from video_pre_training_b200 import parallel
 
     for B in (1, 5, 128):
