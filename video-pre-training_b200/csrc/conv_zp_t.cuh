@@ -194,6 +194,39 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             // thread-per-row mapping -- the L1/shared pipe is what the UMMA operand fetch competes for), and the fp32 tile
             // reads are bank-conflict free.  Each warp does 4 passes per quarter; residual rows are prefetched a quarter ahead.
             const int chunk = lane >> 1, c0 = chunk * 8;
+            // fold tables of the interior border class (cls 4: ~94 % of the rows) for this thread's 8 channels, kept in registers
+            float s1c[8], s2c[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1c[j] = p.S1 ? __ldg(p.S1 + 4 * 128 + c0 + j) : 0.f;
+                s2c[j] = p.S2 ? __ldg(p.S2 + 4 * 128 + c0 + j) : 0.f;
+            }
+            // per-row constants (ga, gb, cls; cls -1 = zero row/column, -2 = beyond the tensor) of quarter hh of tile tl, written by
+            // the first 64 epilogue threads into buffer hh & 1 ONE QUARTER AHEAD of its use (the statistics loads overlap phase B)
+            auto write_info = [&](long long tl, int hh) {
+                if (et >= 64 || tl >= p.num_tiles) return;
+                const long long q = tl * kCtPix + hh * 64 + et;
+                float4 info = make_float4(1.f, 0.f, -2.f, 0.f);
+                if (q < p.Q) {
+                    const unsigned qq = (unsigned)q, f = qq / (unsigned)p.FS, r = qq - f * (unsigned)p.FS;
+                    const int y = (int)(r / (unsigned)p.Wp), x = (int)r - y * p.Wp;
+                    if (y < p.H && x < p.W) {
+                        const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+                        const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+                        float ga = 1.f, gb = 0.f;
+                        if (p.mr) {
+                            const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
+                            ga = rstd;
+                            gb = rstd * mean;
+                        }
+                        info = make_float4(ga, gb, (float)(cy * 3 + cx), 0.f);
+                    } else {
+                        info.z = -1.f;
+                    }
+                }
+                s_info0[(hh & 1) * 64 + et] = info;
+            };
+            if (local == 0) write_info(tile, 0);  // later tiles: written during the previous tile's last quarter
             uint4 rres_n[4];
             auto prefetch_res = [&](int hh) {
                 if (!p.residual) return;
@@ -214,28 +247,6 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 // B(h - 1) -> A(h + 1) on the same buffer.
                 float* s_tile = s_tile0 + (h & 1) * (64 * kCtPitch);
                 float4* s_info = s_info0 + (h & 1) * 64;
-                if (et < 64) {  // per-row constants of this quarter: (ga, gb, cls); cls -1 = zero row/column, -2 = beyond the tensor
-                    const long long q = q0 + h * 64 + et;
-                    float4 info = make_float4(1.f, 0.f, -2.f, 0.f);
-                    if (q < p.Q) {
-                        const unsigned qq = (unsigned)q, f = qq / (unsigned)p.FS, r = qq - f * (unsigned)p.FS;
-                        const int y = (int)(r / (unsigned)p.Wp), x = (int)r - y * p.Wp;
-                        if (y < p.H && x < p.W) {
-                            const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
-                            const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
-                            float ga = 1.f, gb = 0.f;
-                            if (p.mr) {
-                                const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
-                                ga = rstd;
-                                gb = rstd * mean;
-                            }
-                            info = make_float4(ga, gb, (float)(cy * 3 + cx), 0.f);
-                        } else {
-                            info.z = -1.f;
-                        }
-                    }
-                    s_info[et] = info;
-                }
                 if (p.dbg_skip_epilogue != 2) {  // ---- phase A: TMEM -> transposed fp32 tile
                     uint32_t acc[32];
                     const int pl0 = cgrp * 32;
@@ -250,6 +261,8 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (h < 3) write_info(tile, h + 1);
+                else write_info(tile + gridDim.x, 0);
                 if (p.dbg_skip_epilogue == 2) continue;
                 // ---- phase B
 #pragma unroll
@@ -264,12 +277,13 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         if (cls >= 0) {
                             const float4 t0 = *reinterpret_cast<const float4*>(s_tile + prow * kCtPitch + c0);
                             const float4 t1 = *reinterpret_cast<const float4*>(s_tile + prow * kCtPitch + c0 + 4);
-                            float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
-                            if (p.S1) {
+                            float4 a0 = make_float4(s1c[0], s1c[1], s1c[2], s1c[3]), a1 = make_float4(s1c[4], s1c[5], s1c[6], s1c[7]);
+                            float4 b0 = make_float4(s2c[0], s2c[1], s2c[2], s2c[3]), b1 = make_float4(s2c[4], s2c[5], s2c[6], s2c[7]);
+                            if (cls != 4 && p.S1) {
                                 a0 = __ldg(reinterpret_cast<const float4*>(p.S1 + cls * 128 + c0));
                                 a1 = __ldg(reinterpret_cast<const float4*>(p.S1 + cls * 128 + c0) + 1);
                             }
-                            if (p.S2) {
+                            if (cls != 4 && p.S2) {
                                 b0 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0));
                                 b1 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0) + 1);
                             }
