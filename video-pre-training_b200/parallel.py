@@ -50,24 +50,25 @@ class HostFramePipe:
 
     def submit(self, host_img: torch.Tensor, host_first: torch.Tensor):
         i = self.cur
-        # the compute stream may still be reading slot i from two chunks ago: order the overwrite after it
+        # slot i was last read by the forward of two chunks ago, already enqueued on the compute stream: order the overwrite after it
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self.slots[i] is None or self.slots[i][0].shape != host_img.shape:
+            # static device slots (allocated once): no allocator traffic, no implicit synchronisation in the steady state
+            self.slots[i] = (torch.empty(host_img.shape, dtype=host_img.dtype, device=self.device),
+                             torch.empty(host_first.shape, dtype=host_first.dtype, device=self.device))
         with torch.cuda.stream(self.stream):
-            img = host_img.to(self.device, non_blocking=True)
-            first = host_first.to(self.device, non_blocking=True)
+            self.slots[i][0].copy_(host_img, non_blocking=True)
+            self.slots[i][1].copy_(host_first, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self.slots[i], self.events[i] = (img, first), ev
+        self.events[i] = ev
         self.pending = i
         self.cur ^= 1
 
     def take(self):
         i = self.pending
         torch.cuda.current_stream(self.device).wait_event(self.events[i])
-        img, first = self.slots[i]
-        img.record_stream(torch.cuda.current_stream(self.device))
-        first.record_stream(torch.cuda.current_stream(self.device))
-        return img, first
+        return self.slots[i]
 
 
 class FlatAdamDP:
