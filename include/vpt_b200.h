@@ -204,6 +204,15 @@ int vpt_gather_logprob(const float* logits, const int64_t* idx, float* lp, int64
                        void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
+ * Frame ingest (the step before the path: agent.py:100-103,141-149): bilinear uint8 resize, bit-exact with
+ * cv2.resize(..., interpolation=cv2.INTER_LINEAR).  xidx[Wd] / xw[Wd][2] and yidx[Hd] / yw[Hd][2] are the source index and the
+ * 11-bit fixed-point weight pairs per destination column / row (computed on the host the way OpenCV does; see agent.py here).
+ *   src u8 [F][Hs][Ws][C] -> dst u8 [F][Hd][Wd][C]
+ * -------------------------------------------------------------------------------------------------------- */
+int vpt_resize_bilinear_u8(const uint8_t* src, uint8_t* dst, const int32_t* xidx, const int16_t* xw, const int32_t* yidx,
+                           const int16_t* yw, int32_t F, int32_t Hs, int32_t Ws, int32_t Hd, int32_t Wd, int32_t C, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
  * BC step groundwork (behavioural_cloning.py:63-67,119-123): fused torch.optim.Adam(lr, weight_decay) step over ONE flat fp32
  * bucket holding every parameter (gradients in a second flat bucket that data parallelism reduces with a single NCCL
  * all-reduce; grad_scale = 1/world_size).  step counts from 1.  The backward kernels that fill `grads` are not built yet.

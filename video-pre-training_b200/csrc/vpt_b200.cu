@@ -27,6 +27,7 @@ void set_error(const char* fmt, ...) {
 #include "attention.cuh"
 #include "heads.cuh"
 #include "adam.cuh"
+#include "resize.cuh"
 
 extern "C" const char* vpt_last_error(void) { return vpt::g_err; }
 extern "C" int vpt_abi_version(void) { return VPT_ABI_VERSION; }
