@@ -10,6 +10,7 @@ of the forward path runs in csrc/*.cuh behind the C ABI of include/vpt_b200.h.  
 """
 from . import _native  # noqa: F401
 from .types import DictType, Discrete, TensorType, idm_action_space, minecraft_action_space  # noqa: F401
+from .agent import ActionCodec, MineRLAgent, resize_frames  # noqa: F401
 from .policy import InverseActionNet, InverseActionPolicy, MinecraftAgentPolicy, MinecraftPolicy, NetConfig  # noqa: F401
 
 POLICY_KWARGS_2X = dict(  # agent.py:16-36
