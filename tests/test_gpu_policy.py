@@ -187,3 +187,26 @@ def test_graphed_act_matches_eager_and_logit_mask():
     p = pd["buttons"].exp()
     assert torch.allclose(p[..., [3, 77]].sum(-1), torch.ones(B, 1, 1, device=DEV), atol=1e-4)
     nat.device_check()
+
+
+def test_bench_workload_128x128_rows_match_oracle():
+    """The exact bench.py workload (2x width, B=128, T=128 = 16384 frames per chunk, 8 CNN sub-chunks of 2048 frames): two of
+    the 128 sequences are followed by the CPU oracle; rows in different CNN sub-chunks must behave identically."""
+    kw = vpt_b200.policy_kwargs("2x")
+    pol, sd, cfg = make_policy(kw, pert=True, seed=3)
+    pol = pol.to(DEV)
+    B, T = 128, 128
+    g = torch.Generator().manual_seed(17)
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, generator=g)
+    img[77] = img[5]  # the same sequence placed in two different CNN sub-chunks -> bit-identical outputs
+    first = torch.zeros(B, T, dtype=torch.bool)
+    (pd, v, _), st = pol({"img": img.to(DEV)}, first.to(DEV), pol.initial_state(B))
+    nat.device_check()
+    assert torch.equal(pd["buttons"][77], pd["buttons"][5]) and torch.equal(pd["camera"][77], pd["camera"][5])
+    for b in (5, 120):
+        with torch.no_grad():
+            (pd_o, _, _), _ = O.agent_policy_forward(sd, cfg, img[b:b + 1], first[b:b + 1], O.initial_state(cfg, 1))
+        for k in pd_o:
+            e = rel_err(pd[k][b:b + 1].cpu(), pd_o[k])
+            print(f"bench workload row {b} {k}: max rel err {e:.4g}")
+            assert e < RTOL_BF16, (b, k, e)
