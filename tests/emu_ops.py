@@ -223,3 +223,164 @@ def gumbel_argmax(logits, u=None):
 def gather_logprob(logits, idx, lp=None):
     r = logits.gather(-1, idx.long().unsqueeze(-1)).squeeze(-1)
     return r if lp is None else lp + r
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward ops of the BC step (training.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def relu_mask(dout, out):
+    return torch.where(out.float() > 0, dout, torch.zeros_like(dout))
+
+
+def add_zp(a, b, H, W, out=None):
+    """ZP a + b (bf16) with the per-frame statistics of the sum."""
+    s = (a.float() + b.float()).to(BF16)
+    if out is not None:
+        out.copy_(s)
+        s = out
+    return s, _frame_stats(from_zp(s))
+
+
+def transpose(x):
+    R, Cc = x.shape
+    ld = (R + 7) // 8 * 8
+    t = torch.zeros((Cc, ld), dtype=x.dtype)
+    t[:, :R] = x.T
+    return t
+
+
+def wgrad(aT, bT, R, shifts=(0,), out=None):
+    """out[m][tap*N + n] = sum_k aT[m][k] * bT[n][k + shifts[tap]]  (terms with k + shift outside [0, R) are zero); fp32."""
+    M, N = aT.shape[0], bT.shape[0]
+    a = aT[:, :R].float()
+    b = bT[:, :R].float()
+    cols = []
+    for s in shifts:
+        bs = torch.zeros_like(b)
+        if s >= 0:
+            bs[:, :R - s] = b[:, s:]
+        else:
+            bs[:, -s:] = b[:, :R + s]
+        cols.append(a @ bs.T)
+    res = torch.cat(cols, 1)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def _norm_n(x, mr, rows_per_group):
+    Cc = x.shape[-1]
+    xf = x.float().reshape(-1, Cc)
+    g = torch.arange(xf.shape[0]) // rows_per_group
+    return (xf - mr[g, 0:1]) * mr[g, 1:2], g
+
+
+def group_sums(du, x, mr, gamma, rows_per_group, count):
+    """per group: (mean of gamma*du, mean of gamma*du*n) with n = (x - mean) * rstd; `count` = real elements per group."""
+    Cc = x.shape[-1]
+    n, g = _norm_n(x, mr, rows_per_group)
+    dn = du.float().reshape(-1, Cc) * gamma[None]
+    G = n.shape[0] // rows_per_group
+    s1 = dn.double().reshape(G, -1).sum(1) / count
+    s2 = (dn * n).double().reshape(G, -1).sum(1) / count
+    return torch.stack([s1, s2], 1).float()
+
+
+def col_sums(du, x=None, mr=None, rows_per_group=1):
+    """fp32 [2][C]: (sum_rows du*n, sum_rows du); without x only row 1 is meaningful (row 0 = 0)."""
+    Cc = du.shape[-1]
+    d = du.float().reshape(-1, Cc)
+    out = torch.zeros((2, Cc), dtype=F32)
+    out[1] = d.double().sum(0).float()
+    if x is not None:
+        n, _ = _norm_n(x, mr, rows_per_group)
+        out[0] = (d * n).double().sum(0).float()
+    return out
+
+
+def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None):
+    """dx = rstd * (gamma*du - m1 - n*m2) [+ add] on [rows][C]; with zp = (H, W, Cch) every group is a ZP frame
+    [(H+1)(W+1)][Cch] (flattened over rows_per_group rows of C) whose pad row / column is written as zero."""
+    Cc = x.shape[-1]
+    n, g = _norm_n(x, mr, rows_per_group)
+    dn = du.float().reshape(-1, Cc) * gamma[None]
+    dx = mr[g, 1:2] * (dn - ms[g, 0:1] - n * ms[g, 1:2])
+    if add is not None:
+        dx = dx + add.float().reshape(-1, Cc)
+    dx = dx.to(BF16)
+    if zp is not None:
+        H, W, Cch = zp
+        e = torch.arange(rows_per_group * Cc) // Cch          # pixel row inside the frame
+        pad = ((e // (W + 1)) == H) | ((e % (W + 1)) == W)
+        dx = torch.where(pad.reshape(1, -1), torch.zeros((), dtype=BF16), dx.reshape(-1, rows_per_group * Cc))
+    return dx.reshape(x.shape)
+
+
+def maxpool3s2_bwd(dy, x, y):
+    """Gradient of max_pool2d(3,2,1) (+ the ReLU in front of it: x is post-ReLU) on ZP tensors; first maximum wins ties."""
+    xi = from_zp(x).float().permute(0, 3, 1, 2).requires_grad_(True)
+    yo = F.max_pool2d(xi, 3, 2, 1)
+    (g,) = torch.autograd.grad(yo, xi, from_zp(dy).float().permute(0, 3, 1, 2))
+    g = torch.where(xi > 0, g, torch.zeros_like(g))
+    return to_zp(g.permute(0, 2, 3, 1).contiguous().to(BF16))
+
+
+def firstconv_bwd(img, w, bias, dy, C0):
+    """(dW fp32 [C0][27] in the kernel's (ky,kx,c) order for the /255-scaled weights, db [C0])."""
+    x = img.float().permute(0, 3, 1, 2)
+    wt = w.reshape(C0, 3, 3, 3).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    b = bias.clone().requires_grad_(True)
+    y = F.max_pool2d(F.relu(F.conv2d(x, wt, b, padding=1)), 3, 2, 1)
+    gw, gb = torch.autograd.grad(y, (wt, b), from_zp(dy).float().permute(0, 3, 1, 2))
+    return gw.permute(0, 2, 3, 1).reshape(C0, 27).contiguous(), gb
+
+
+def attention_bwd(Q, Kf, Vf, R, b_nd, first_u8, smask, dO, out, B, t, maxlen, heads, causal=True):
+    """Gradients of `attention` wrt Q, the chunk rows of K / V and R, written side by side into out[:, 0:h | h:2h | 2h:3h |
+    3h:3h+10*heads] (bf16); returns d b_nd (fp32).  The memory rows of K / V are detached state and get no gradient."""
+    h = Q.shape[-1]
+    D = h // heads
+    T = maxlen + t
+    q = Q.float().reshape(B, t, heads, D).permute(0, 2, 1, 3).requires_grad_(True)
+    kf = Kf.float().requires_grad_(True)
+    vf = Vf.float().requires_grad_(True)
+    k = kf.reshape(B, T, heads, D).permute(0, 2, 1, 3)
+    v = vf.reshape(B, T, heads, D).permute(0, 2, 1, 3)
+    Rf = R.float().requires_grad_(True) if R is not None else None
+    bf = b_nd.float().requires_grad_(True) if causal else None
+    logit = q @ k.transpose(-1, -2) / D
+    if causal:
+        i = torch.arange(t)[:, None]
+        j = torch.arange(T)[None, :]
+        d = maxlen + i - j
+        band = (d >= 0) & (d < maxlen)
+        memok = torch.zeros(B, maxlen, dtype=torch.bool) if smask is None else (smask.reshape(B, maxlen) != 0)
+        memok = memok & (first_u8[:, 0] == 0)[:, None]
+        colok = torch.cat([memok, torch.ones(B, t, dtype=torch.bool)], 1)
+        allowed = band[None] & colok[:, None, :]
+        E = Rf.reshape(B, t, heads, -1).permute(0, 2, 1, 3) @ bf
+        dd = d.clamp(0, maxlen - 1)[None, None].expand(B, heads, t, T)
+        extra = torch.gather(E, 3, dd)
+        logit = torch.where(allowed[:, None], logit + extra, torch.tensor(-float("inf")))
+    w = torch.softmax(logit, -1)
+    o = (w @ v).permute(0, 2, 1, 3).reshape(B * t, h)
+    ins = [q, kf, vf] + ([Rf, bf] if causal else [])
+    gs = torch.autograd.grad(o, ins, dO.float().reshape(B * t, h))
+    out[:, 0:h] = gs[0].permute(0, 2, 1, 3).reshape(B * t, h).to(BF16)
+    out[:, h:2 * h] = gs[1][:, maxlen:].reshape(B * t, h).to(BF16)
+    out[:, 2 * h:3 * h] = gs[2][:, maxlen:].reshape(B * t, h).to(BF16)
+    if causal:
+        nr = R.shape[-1]
+        out[:, 3 * h:3 * h + nr] = gs[3].reshape(B * t, nr).to(BF16)
+        return gs[4].contiguous()
+    return None
+
+
+def softmax_bwd(logp, idx, scale, out, col0):
+    """out[:, col0:col0+n] = (exp(logp) - onehot(idx)) * scale   (bf16)."""
+    n = logp.shape[-1]
+    g = torch.exp(logp.float().reshape(-1, n))
+    g[torch.arange(g.shape[0]), idx.reshape(-1).long()] -= 1.0
+    out[:, col0:col0 + n] = (g * scale).to(out.dtype)
+    return out

@@ -243,3 +243,151 @@ def gather_logprob(logits, idx, lp=None):
     nat.check(nat.lib().vpt_gather_logprob(_p(logits), _p(idx), _p(lp), rows, n, int(acc), _stream()), "vpt_gather_logprob")
     _count()
     return lp
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward ops of the BC step (training.py; behavioural_cloning.py:101-123)
+# ---------------------------------------------------------------------------------------------------------------------
+def relu_mask(dout, out):
+    """dz = dout where the ReLU was open (out > 0), else 0 (bf16, any shape)."""
+    _cuda(dout, out)
+    dz = torch.empty_like(dout)
+    nat.check(nat.lib().vpt_relu_mask(_p(dout), _p(out), _p(dz), dout.numel(), _stream()), "vpt_relu_mask")
+    _count()
+    return dz
+
+
+def add_zp(a, b, H, W, out=None):
+    """ZP a + b -> (bf16 ZP sum, per-frame (mean, rstd) of the sum): the residual add of a training forward."""
+    _cuda(a, b)
+    F_, Cc = a.shape[0], a.shape[3]
+    if out is None:
+        out = torch.empty_like(a)
+    per = (H + 1) * (W + 1) * Cc
+    P = nat.lib().vpt_add_stat_parts(per)
+    part = torch.empty((F_, P, 2), dtype=F32, device=a.device)
+    nat.check(nat.lib().vpt_add_stats(_p(a), _p(b), _p(out), _p(part), F_, per, _stream()), "vpt_add_stats")
+    _count()
+    return out, stats_finalize(part, F_, P, H * W * Cc)
+
+
+def transpose(x):
+    """bf16 [R][C] -> [C][ld], ld = R rounded up to 8 (zero tail): the K-major operand layout of `wgrad`."""
+    _cuda(x)
+    R, Cc = x.shape
+    ld = (R + 7) // 8 * 8
+    out = torch.empty((Cc, ld), dtype=BF16, device=x.device)
+    nat.check(nat.lib().vpt_transpose_bf16(_p(x), _p(out), R, Cc, x.stride(0), ld, _stream()), "vpt_transpose_bf16")
+    _count()
+    return out
+
+
+def wgrad(aT, bT, R, shifts=(0,), out=None):
+    """fp32 out[m][tap*N + n] = sum_k aT[m][k] * bT[n][k + shifts[tap]] over k in [0, R) (out-of-range terms are zero)."""
+    _cuda(aT, bT)
+    M, N, ld = aT.shape[0], bT.shape[0], aT.shape[1]
+    assert bT.shape[1] == ld and aT.is_contiguous() and bT.is_contiguous()
+    nt = len(shifts)
+    if out is None:
+        out = torch.empty((M, nt * N), dtype=F32, device=aT.device)
+    ws_bytes = nat.lib().vpt_wgrad_workspace_bytes(M, N, nt, R)
+    ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=F32, device=aT.device)
+    sh = (C.c_int32 * nt)(*[int(s) for s in shifts])
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    nat.check(nat.lib().vpt_wgrad_bf16(_p(aT), _p(bT), M, N, R, ld, sh, nt, _p(out), _p(ws), ws_bytes, _stream()), "vpt_wgrad_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * nt * R, "wgrad", (M, nt * N, R)))
+    _count(2)
+    return out
+
+
+def group_sums(du, x, mr, gamma, rows_per_group, count):
+    """fp32 [G][2]: per statistics group (mean of gamma*du, mean of gamma*du*n), n = (x - mean) * rstd; du, x bf16 [rows][C]."""
+    _cuda(du, x, mr, gamma)
+    rows, Cc = x.shape
+    G = rows // rows_per_group
+    P = nat.lib().vpt_group_sums_parts(rows_per_group, Cc)
+    part = torch.empty((G, P, 2), dtype=F32, device=x.device)
+    ms = torch.empty((G, 2), dtype=F32, device=x.device)
+    nat.check(nat.lib().vpt_group_sums(_p(du), _p(x), _p(mr), _p(gamma), _p(part), _p(ms), rows, Cc, rows_per_group, float(count),
+                                       _stream()), "vpt_group_sums")
+    _count(2)
+    return ms
+
+
+def col_sums(du, x=None, mr=None, rows_per_group=1):
+    """fp32 [2][C]: (sum_rows du*n, sum_rows du); without x row 0 is zero.  du (and x) bf16 [rows][C] (row stride allowed)."""
+    _cuda(du, x, mr)
+    rows, Cc = du.shape
+    out = torch.empty((2, Cc), dtype=F32, device=du.device)
+    S = nat.lib().vpt_col_sums_parts(rows, Cc)
+    ws = torch.empty((S, 2, Cc), dtype=F32, device=du.device)
+    nat.check(nat.lib().vpt_col_sums(_p(du), du.stride(0), _p(x), _p(mr), rows, Cc, rows_per_group, _p(out), _p(ws), _stream()), "vpt_col_sums")
+    _count(2)
+    return out
+
+
+def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None):
+    """dx = rstd * (gamma*du - m1 - n*m2) [+ add] (bf16 [rows][C]); zp = (H, W, Cch): groups are ZP frames, pads written as 0."""
+    _cuda(du, x, mr, gamma, ms, add)
+    rows, Cc = x.shape
+    dx = torch.empty_like(x)
+    H, W, Cch = zp if zp is not None else (0, 0, 0)
+    nat.check(nat.lib().vpt_norm_bwd_apply(_p(du), _p(x), _p(mr), _p(gamma), _p(ms), _p(add), _p(dx), rows, Cc, rows_per_group, H, W, Cch,
+                                           _stream()), "vpt_norm_bwd_apply")
+    _count()
+    return dx
+
+
+def maxpool3s2_bwd(dy, x, y):
+    """Gradient of ReLU -> max_pool2d(3, 2, 1) on ZP tensors: dy, y [F,H/2+1,W/2+1,C], x (post-ReLU pool input) [F,H+1,W+1,C]."""
+    _cuda(dy, x, y)
+    F_, H, W, Cc = x.shape[0], x.shape[1] - 1, x.shape[2] - 1, x.shape[3]
+    dx = torch.empty_like(x)
+    nat.check(nat.lib().vpt_maxpool3s2_bwd(_p(dy), _p(x), _p(y), _p(dx), F_, H, W, Cc, _stream()), "vpt_maxpool3s2_bwd")
+    _count()
+    return dx
+
+
+def firstconv_bwd(img, w, bias, dy, C0):
+    """Weight / bias gradient of the fused first conv + ReLU + max-pool: (fp32 [C0][27] in (ky,kx,c) order, fp32 [C0])."""
+    _cuda(img, w, bias, dy)
+    F_, H, W, _ = img.shape
+    S = nat.lib().vpt_firstconv_bwd_parts(F_, H, W)
+    ws = torch.empty((S, C0, 28), dtype=F32, device=img.device)
+    dW = torch.empty((C0, 27), dtype=F32, device=img.device)
+    db = torch.empty((C0,), dtype=F32, device=img.device)
+    nat.check(nat.lib().vpt_firstconv_bwd(_p(img), _p(w), _p(bias), _p(dy), _p(dW), _p(db), _p(ws), F_, H, W, C0, _stream()), "vpt_firstconv_bwd")
+    _count(2)
+    return dW, db
+
+
+def attention_bwd(Q, Kf, Vf, R, b_nd, first_u8, smask, dO, out, B, t, maxlen, heads, causal=True):
+    """Backward of `attention`: d q | d k | d v | d R written side by side into out[:, 0:h | h:2h | 2h:3h | 3h:3h+10*heads]
+    (bf16, chunk rows only: the KV memory is detached state); returns d b_nd fp32 [nbasis][maxlen]."""
+    _cuda(Q, Kf, Vf, R, b_nd, dO, out)
+    if not causal:
+        raise NotImplementedError("attention_bwd: only the causal policy attention is trained")
+    nbasis = b_nd.shape[0]
+    T = maxlen + t
+    ws = torch.empty((2, B * heads, t, T), dtype=F32, device=Q.device)  # P and dS
+    db = torch.empty((nbasis, maxlen), dtype=F32, device=Q.device)
+    nat.check(nat.lib().vpt_attention_bwd(_p(Q), _p(Kf), _p(Vf), _p(R), R.stride(-2), _p(b_nd), _p(first_u8), first_u8.stride(0), _p(smask),
+                                          _p(dO), _p(out), out.stride(0), _p(db), _p(ws), B, t, maxlen, heads, nbasis, _stream()),
+              "vpt_attention_bwd")
+    _count(3)
+    return db
+
+
+def softmax_bwd(logp, idx, scale, out, col0):
+    """out[:, col0:col0+n] = (exp(logp) - onehot(idx)) * scale  (bf16): d loss / d logits of a categorical NLL head."""
+    _cuda(logp, idx, out)
+    rows, n = logp.shape
+    nat.check(nat.lib().vpt_softmax_bwd(_p(logp.contiguous()), _p(idx.contiguous()), float(scale), _p(out), out.stride(0), col0, rows, n, _stream()),
+              "vpt_softmax_bwd")
+    _count()
+    return out

@@ -289,6 +289,7 @@ class MinecraftPolicy(nn.Module):
         self._prep = None
         self._prep_fp = None
         self.debug_taps = None  # set to a dict to capture intermediate activations (tests)
+        self._tape = None       # set to a dict by training.BCTrainer: the forward then records what the backward needs
 
     def output_latent_size(self):
         return self.hidsize
@@ -321,22 +322,28 @@ class MinecraftPolicy(nn.Module):
         cfg = self.cfg
         H, W = cfg.img_shape[0], cfg.img_shape[1]
         x, mr = None, None
+        tape = self._tape
         if prep.conv3d is not None:  # IDM: img is (b, T, H, W, 3), whole sequences (the temporal conv needs its neighbours)
             x, mr = ops.conv3d_t5(img, prep.conv3d[0], prep.conv3d[1], cfg.conv3d_out)
             self._tap("conv3d", x)
         for i, c in enumerate(cfg.chans):
             st = prep.stacks[i]
+            rec = dict(x_in=x, mr_in=mr, H_in=H, W_in=W, full=None, blocks=[]) if tape is not None else None
             if i == 0 and "fc_w" in st:
                 y1, mr1 = ops.firstconv_pool(img, st["fc_w"], st["fc_b"], c, zp=True)
             else:
                 Wb, S1, S2 = st["first"]
                 full, _ = ops.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, want_stats=False)
                 y1, mr1 = ops.maxpool3s2(full, zp=True)
+                if rec is not None:
+                    rec["full"] = full
                 del full
             H, W = H // 2, W // 2
             self._tap(f"{pfx}.stacks.{i}.pool", y1)
             # post-pool GroupNorm `n` (lib/impala_cnn.py:119): materialised because it is the residual stream
             x, mr = ops.affine_norm_zp(y1, mr1, st["n_g"], st["n_b"])
+            if rec is not None:
+                rec.update(y1=y1, mr1=mr1, x0=x, mr0=mr)
             del y1
             self._tap(f"{pfx}.stacks.{i}.n", x)
             for j in range(2):
@@ -345,17 +352,26 @@ class MinecraftPolicy(nn.Module):
                 self._tap(f"{pfx}.stacks.{i}.blocks.{j}.conv0", hmid)
                 Wb, S1, S2 = st["convs"][2 * j + 1]
                 last = (i == len(cfg.chans) - 1) and j == 1
-                x, mr = ops.conv3x3_zp(hmid, Wb, H, W, mr=mrh, S1=S1, S2=S2, relu=1, residual=x, out=out if last else None)
+                if rec is None:
+                    x, mr = ops.conv3x3_zp(hmid, Wb, H, W, mr=mrh, S1=S1, S2=S2, relu=1, residual=x, out=out if last else None)
+                else:
+                    # training: the branch output r = relu(conv1(..)) is kept on its own (its sign pattern IS the ReLU mask the
+                    # backward needs; x + r rounded to bf16 no longer shows which small r were positive), then added
+                    r, _ = ops.conv3x3_zp(hmid, Wb, H, W, mr=mrh, S1=S1, S2=S2, relu=1, want_stats=False)
+                    x, mr = ops.add_zp(x, r, H, W, out=out if last else None)
+                    rec["blocks"].append(dict(h=hmid, mrh=mrh, r=r, x=x, mr=mr))
                 self._tap(f"{pfx}.stacks.{i}.blocks.{j}", x)
+            if rec is not None:
+                tape["stacks"].append(rec)
         return x, mr
 
     # -- transformer -----------------------------------------------------------------------------------------
-    def _linear(self, x, fold, N, *, mr=None, relu=0, residual=None, out=None, out_dtype=BF16, seg=None, want_stats=False,
+    def _linear(self, x, fold, N, *, mr=None, relu=0, residual=None, out=None, out_dtype=None, seg=None, want_stats=False,
                 out_scale=1.0, ld_out=None):
         Wb, S1, S2 = fold
         M, K = x.shape[0], x.shape[1]
         if out is None:
-            out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+            out = torch.empty((M, N), dtype=out_dtype or BF16, device=x.device)
         part, P = None, ops.gemm_stat_parts(N)
         if want_stats:
             part = torch.empty((M, P, 2), dtype=F32, device=x.device)
@@ -400,6 +416,9 @@ class MinecraftPolicy(nn.Module):
         z, mr_z = self._linear(hmid, L["mlp1"], h, residual=y, relu=2 if last else 0, want_stats=True)
         if not last:
             self._tap(f"recurrent_layer.blocks.{l}", z)
+        if self._tape is not None:
+            self._tape["blocks"].append(dict(x=x, mr_x=mr_x, xhat=xhat, q=q, full_k=full_k, full_v=full_v, R=R, smask=smask_u8, a=a, y=y,
+                                             mr_y=mr_y, hmid=hmid, z=z, mr_z=mr_z))
         return z, mr_z, (new_mask, (new_k, new_v))
 
     # -- whole net -------------------------------------------------------------------------------------------
@@ -435,10 +454,17 @@ class MinecraftPolicy(nn.Module):
         mr_c = mrs[0] if len(mrs) == 1 else torch.cat(mrs, 0)
         Kd = (Hf + 1) * (Wf + 1) * C2  # ZP rows flattened; the zero row / column meets zero weight columns
         xd, mr_d = self._linear(cnn_out.view(N, Kd), prep.dense, cfg.cnn_outsize, mr=mr_c, relu=1, want_stats=True)
+        tape = self._tape
+        if tape is not None:
+            if len(mrs) != 1:
+                raise NotImplementedError(f"training forward: at most {step} frames per call (got {N})")
+            tape.update(frames=frames, first_u8=first_u8, cnn_out=cnn_out, mr_c=mr_c, xd=xd, mr_d=mr_d)
         del cnn_out
         self._tap("img_process.cnn.dense", xd)
         x, mr_x = self._linear(xd, prep.linear, cfg.hidsize, mr=mr_d, relu=1, want_stats=True)
         self._tap("img_process", x)
+        if tape is not None:
+            tape.update(x0=x, mr_x0=mr_x)
         # ---- transformer
         state_out = []
         for l in range(cfg.n_layers):
@@ -446,7 +472,10 @@ class MinecraftPolicy(nn.Module):
             state_out.append(s)
         # x is relu(recurrent output) here
         if use_lastlayer:
+            z_last, mr_zl = x, mr_x
             x, mr_x = self._linear(x, prep.last, cfg.hidsize, mr=mr_x, relu=1, want_stats=True)
+            if tape is not None:
+                tape.update(z_last=z_last, mr_zl=mr_zl, xl=x, mr_xl=mr_x)
         lat_bf16, lat_f32, _ = ops.affine_norm(x, mr_x, prep.fin_g, prep.fin_b, rows_per_group=1, want_f32=True)
         return lat_bf16, lat_f32.view(B, t, cfg.hidsize), state_out
 
