@@ -215,10 +215,63 @@ int vpt_resize_bilinear_u8(const uint8_t* src, uint8_t* dst, const int32_t* xidx
 /* ----------------------------------------------------------------------------------------------------------
  * BC step groundwork (behavioural_cloning.py:63-67,119-123): fused torch.optim.Adam(lr, weight_decay) step over ONE flat fp32
  * bucket holding every parameter (gradients in a second flat bucket that data parallelism reduces with a single NCCL
- * all-reduce; grad_scale = 1/world_size).  step counts from 1.  The backward kernels that fill `grads` are not built yet.
+ * all-reduce; grad_scale = 1/world_size).  step counts from 1.  The kernels below fill `grads`.
  * -------------------------------------------------------------------------------------------------------- */
 int vpt_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, float grad_scale, int32_t step, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * BC step backward (behavioural_cloning.py:101-123; the reference gets it from autograd over lib/policy.py).  The host side
+ * (video-pre-training_b200/training.py) chains these with the forward entry points above: d(input) of a convolution / linear is
+ * vpt_conv3x3_zp / vpt_gemm_bf16 on rotated / transposed weights; the rest is here.  With u = gamma*n + beta, n = (x-mean)*rstd:
+ * -------------------------------------------------------------------------------------------------------- */
+/* ReLU backward: dz = dout where out > 0, else 0 (bf16, n elements, n % 8 == 0)            lib/util.py:81 */
+int vpt_relu_mask(const void* dout, const void* out, void* dz, int64_t n, void* stream);
+/* Residual add of the training forward, out = a + b (bf16) per group of `elems_per_group` elements, with float2 (sum, sumsq)
+ * partials [groups][vpt_add_stat_parts()] of the stored values (the branch output b is kept separately because its sign
+ * pattern is the ReLU mask the backward needs)                                              lib/impala_cnn.py:50-52 */
+int vpt_add_stats(const void* a, const void* b, void* out, float* stat_part, int64_t groups, int64_t elems_per_group, void* stream);
+int vpt_add_stat_parts(int64_t elems_per_group);
+/* Weight gradient on the tcgen05 GEMM (csrc/gemm_tc.cuh with both operands MN-major, K split over CTAs + fixed-order reduction):
+ *   out fp32 [M][ntaps*N],  out[m][tap*N + n] = sum_{k in [0,R)} a[k][m] * b[k + shifts[tap]][n]   (rows outside [0,R) are 0)
+ * a bf16 [R][lda] = output gradient (M columns), b bf16 [R][ldb] = (normalised) layer input (N columns); no transposes needed.
+ * Linear: ntaps = 1, shift 0.  3x3 conv on ZP tensors: ntaps = 9, shifts[tap] = (ky-1)*(W+1) + (kx-1), out is [Cout][tap][Cin].
+ * workspace: vpt_wgrad_workspace_bytes() bytes (0 when no K split is used). */
+int vpt_wgrad_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t M, int32_t N, int64_t R, const int32_t* shifts,
+                   int32_t ntaps, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t vpt_wgrad_workspace_bytes(int32_t M, int32_t N, int32_t ntaps, int64_t R);
+/* GroupNorm(1) / LayerNorm backward in three passes over du, x bf16 [rows][C] (groups of rows_per_group rows, mr [G][2]):
+ *   vpt_group_sums     ms[g] = (mean gamma*du, mean gamma*du*n) over the group (`count` real elements; part: [G][parts] float2)
+ *   vpt_col_sums       out fp32 [2][C] = (sum_rows du*n, sum_rows du) = (d gamma, d beta); x == NULL: row 1 only (bias gradients);
+ *                      workspace [vpt_col_sums_parts()][2][C] floats
+ *   vpt_norm_bwd_apply dx = rstd * (gamma*du - ms.x - n*ms.y) [+ add]; zpC > 0: every group is a ZP frame [(zpH+1)(zpW+1)][zpC]
+ *                      and its pad row / column is written as zero                          lib/util.py:44-63 (norm placement) */
+int vpt_group_sums(const void* du, const void* x, const float* mr, const float* gamma, float* part, float* ms, int64_t rows, int32_t C,
+                   int32_t rows_per_group, double count, void* stream);
+int vpt_group_sums_parts(int32_t rows_per_group, int32_t C);
+int vpt_col_sums(const void* du, int64_t ld_du, const void* x, const float* mr, int64_t rows, int32_t C, int32_t rows_per_group, float* out,
+                 float* workspace, void* stream);
+int vpt_col_sums_parts(int64_t rows, int32_t C);
+int vpt_norm_bwd_apply(const void* du, const void* x, const float* mr, const float* gamma, const float* ms, const void* add, void* dx,
+                       int64_t rows, int32_t C, int32_t rows_per_group, int32_t zpH, int32_t zpW, int32_t zpC, void* stream);
+/* Backward of ReLU -> max_pool2d(3, 2, 1) on ZP tensors (H, W = pool input size): dx[F][H+1][W+1][C] from dy, y [F][H/2+1][W/2+1][C]
+ * and the post-ReLU pool input x; the first maximum in window scan order takes the gradient     lib/impala_cnn.py:115-117 */
+int vpt_maxpool3s2_bwd(const void* dy, const void* x, const void* y, void* dx, int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
+/* Weight / bias gradient of vpt_firstconv_pool (recomputes the pre-pool map): dW fp32 [C0][27] (same (ky,kx,c) order and /255 scale
+ * as w), db [C0]; dy bf16 ZP [F][H/2+1][W/2+1][C0]; workspace [vpt_firstconv_bwd_parts()][C0][28] floats */
+int vpt_firstconv_bwd(const uint8_t* img, const float* w, const float* bias, const void* dy, float* dW, float* db, float* workspace, int64_t F,
+                      int32_t H, int32_t W, int32_t C0, void* stream);
+int vpt_firstconv_bwd_parts(int64_t F, int32_t H, int32_t W);
+/* Backward of vpt_attention (causal policy attention): given dO bf16 [B*t][h] writes d q | d k | d v | d R side by side into
+ * out bf16 [B*t][ld_out] at columns 0 | h | 2h | 3h (chunk rows only -- the KV memory is detached state,
+ * behavioural_cloning.py:111) and d b_nd fp32 [nbasis][maxlen].  workspace: 2*B*heads*t*maxlen floats.   lib/xf.py:18-71,265-271 */
+int vpt_attention_bwd(const void* Q, const void* Kf, const void* Vf, const float* R, int64_t ld_r, const float* b_nd, const uint8_t* first,
+                      int64_t first_stride, const uint8_t* smask, const void* dO, void* out, int64_t ld_out, float* db_nd, float* workspace,
+                      int32_t B, int32_t t, int32_t maxlen, int32_t heads, int32_t nbasis, void* stream);
+/* d loss / d logits of a categorical NLL head: out[r][col0 + j] = (exp(logp[r][j]) - [j == idx[r]]) * scale  (bf16)
+ *                                                                                          lib/action_head.py:176-184 */
+int vpt_softmax_bwd(const float* logp, const int64_t* idx, float scale, void* out, int64_t ld_out, int32_t col0, int64_t rows, int32_t n,
+                    void* stream);
 
 #ifdef __cplusplus
 }

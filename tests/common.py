@@ -62,3 +62,24 @@ def run_chunks(pol, sd, cfg, B, chunks, dev, first_at=None, seed=0, taps=False):
         out.append(dict(pd=pd, v=v, st=st, pd_o=pd_o, v_o=v_o, st_o=st_o, taps=dict(pol.net.debug_taps or {}), taps_o=to))
     pol.net.debug_taps = None
     return out
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def emulation():
+    """Temporarily route video_pre_training_b200.ops through the test-only torch emulation (CPU tensors)."""
+    import emu_ops
+    from video_pre_training_b200 import ops
+
+    saved = {}
+    for name in dir(emu_ops):
+        if not name.startswith("_") and callable(getattr(emu_ops, name)) and hasattr(ops, name):
+            saved[name] = getattr(ops, name)
+            setattr(ops, name, getattr(emu_ops, name))
+    try:
+        yield
+    finally:
+        for name, fn in saved.items():
+            setattr(ops, name, fn)

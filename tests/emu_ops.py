@@ -241,27 +241,18 @@ def add_zp(a, b, H, W, out=None):
     return s, _frame_stats(from_zp(s))
 
 
-def transpose(x):
-    R, Cc = x.shape
-    ld = (R + 7) // 8 * 8
-    t = torch.zeros((Cc, ld), dtype=x.dtype)
-    t[:, :R] = x.T
-    return t
-
-
-def wgrad(aT, bT, R, shifts=(0,), out=None):
-    """out[m][tap*N + n] = sum_k aT[m][k] * bT[n][k + shifts[tap]]  (terms with k + shift outside [0, R) are zero); fp32."""
-    M, N = aT.shape[0], bT.shape[0]
-    a = aT[:, :R].float()
-    b = bT[:, :R].float()
+def wgrad(a, b, shifts=(0,), out=None):
+    """out[m][tap*N + n] = sum_k a[k][m] * b[k + shifts[tap]][n]  (rows k + shift outside [0, R) are zero); fp32."""
+    R = a.shape[0]
+    af, bf = a.float(), b.float()
     cols = []
     for s in shifts:
-        bs = torch.zeros_like(b)
+        bs = torch.zeros_like(bf)
         if s >= 0:
-            bs[:, :R - s] = b[:, s:]
+            bs[:R - s] = bf[s:]
         else:
-            bs[:, -s:] = b[:, :R + s]
-        cols.append(a @ bs.T)
+            bs[-s:] = bf[:R + s]
+        cols.append(af.T @ bs)
     res = torch.cat(cols, 1)
     if out is not None:
         out.copy_(res)

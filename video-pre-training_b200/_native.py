@@ -98,6 +98,22 @@ SIGNATURES = {
     "vpt_gather_logprob": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "vpt_resize_bilinear_u8": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vpt_adam_step": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _I, _P]),
+    # BC backward (training.py)
+    "vpt_relu_mask": (_I, [_P, _P, _P, _L, _P]),
+    "vpt_add_stats": (_I, [_P, _P, _P, _P, _L, _L, _P]),
+    "vpt_add_stat_parts": (_I, [_L]),
+    "vpt_wgrad_bf16": (_I, [_P, _L, _P, _L, _I, _I, _L, C.POINTER(C.c_int32), _I, _P, _P, _L, _P]),
+    "vpt_wgrad_workspace_bytes": (_L, [_I, _I, _I, _L]),
+    "vpt_group_sums": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _D, _P]),
+    "vpt_group_sums_parts": (_I, [_I, _I]),
+    "vpt_col_sums": (_I, [_P, _L, _P, _P, _L, _I, _I, _P, _P, _P]),
+    "vpt_col_sums_parts": (_I, [_L, _I]),
+    "vpt_norm_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
+    "vpt_maxpool3s2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "vpt_firstconv_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "vpt_firstconv_bwd_parts": (_I, [_L, _I, _I]),
+    "vpt_attention_bwd": (_I, [_P, _P, _P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vpt_softmax_bwd": (_I, [_P, _P, _F, _P, _L, _I, _L, _I, _P]),
 }
 
 _lib = None

@@ -237,10 +237,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;             // SWIZZLE_128B
     return d;
 }
+// MN-major, 128-byte-swizzled operand tile (the operand's M / N index is the contiguous one in memory): every K row holds 64
+// consecutive M/N elements (128 B), 8-K-row groups are 1024 B apart (SBO) and the next 64 M/N elements start `lbo_bytes`
+// further (LBO) -- i.e. TMA boxes of {64 elements (inner), K rows} stored back to back.  Canonical layout per the CUTLASS
+// UMMA notes: Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with both operands MN-major (bits 15 / 16: transpose A / B)
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (quarter*32+i), columns c..c+31.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {

@@ -44,6 +44,11 @@ struct GemmParams {
     long long seg_stride, seg_off;
     float* stat_part;
     int stat_mode;
+    // weight-gradient mode (kWgrad): out[split][m][tap*N + n] = sum over this split's K rows of A[k][m] * B[k + tap_shift[tap]][n]
+    // (both operands MN-major: A is [K rows][M], B is [K rows][N] in memory)
+    int ntaps, k_splits, k_iters_split;
+    int tap_shift[9];
+    long long split_stride;
 };
 
 __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int num_stages) {
@@ -53,6 +58,11 @@ __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int num_sta
     }
 }
 
+// kWgrad: both operands are MN-major -- A = [K rows][M], B = [K rows][N] row-major activations (K = pixels / tokens), staged
+// as TMA boxes of {64 columns, 64 K rows} -- the tile index additionally enumerates (K split, tap); tiles are
+// [split][m_tile][tap][n_tile] and the B operand is read `tap_shift[tap]` rows further down (TMA zero-fills what falls outside
+// the tensor, which is exactly the zero padding of a 3x3 convolution on the ZP layout).  cluster == 1 in this mode.
+template <bool kWgrad>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -101,7 +111,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cluster_id = blockIdx.x / CS, num_clusters = gridDim.x / CS;
     const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
     // a "super tile" = CS consecutive M tiles of one N tile; CTA r of the cluster owns M tile group*CS + r
-    const int num_super = ((p.num_m_tiles + CS - 1) / CS) * p.num_n_tiles;
+    const int tiles_mn = ((p.num_m_tiles + CS - 1) / CS) * p.num_n_tiles * (kWgrad ? p.ntaps : 1);
+    const int num_super = tiles_mn * (kWgrad ? p.k_splits : 1);
+    const int n_cols = kWgrad ? p.num_n_tiles * p.ntaps : p.num_n_tiles;  // tile columns (wgrad: [tap][n_tile])
 
     if (warp == 0) {
         if (lane == 0) {
@@ -111,18 +123,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bool ok = true;
             const uint32_t slice_rows = (uint32_t)p.block_n / CS, slice_bytes = stage_bytes_b / CS;
             for (int st = cluster_id; st < num_super && ok; st += num_clusters) {
-                const int m_tile = (st / p.num_n_tiles) * CS + cta_rank, n_tile = st % p.num_n_tiles;
+                const int split = kWgrad ? st / tiles_mn : 0, sm = kWgrad ? st - split * tiles_mn : st;
+                const int m_tile = (sm / n_cols) * CS + cta_rank, col = sm % n_cols;
+                const int tap = kWgrad ? col / p.num_n_tiles : 0, n_tile = kWgrad ? col - tap * p.num_n_tiles : col;
                 const int m0 = m_tile * kBlockM, n0 = n_tile * p.block_n;
                 int f0 = 0, y0 = 0;
                 if (p.conv) {
                     f0 = m0 / p.px_per_frame;
                     y0 = (m0 % p.px_per_frame) / p.W;
                 }
-                for (int it = 0; it < p.k_iters; ++it) {
+                const int it0 = kWgrad ? split * p.k_iters_split : 0;
+                const int it1 = kWgrad ? min(p.k_iters, it0 + p.k_iters_split) : p.k_iters;
+                const int bshift = kWgrad ? p.tap_shift[tap] : 0;
+                for (int it = it0; it < it1; ++it) {
                     if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1u, 0x100u))) break;
                     mbar_expect_tx(&full_bar[stage], kStageBytesA + stage_bytes_b);
                     uint8_t* sa = smem_a + (size_t)stage * kStageBytesA;
                     uint8_t* sb = smem_b + (size_t)stage * stage_bytes_b;
+                    if (kWgrad) {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], m0, it * kBlockK);
+                        tma_load_2d(sa + 8192, &tmA, &full_bar[stage], m0 + 64, it * kBlockK);
+                        for (int bx = 0; bx < p.block_n / 64; ++bx)
+                            tma_load_2d(sb + bx * 8192, &tmB, &full_bar[stage], n0 + bx * 64, it * kBlockK + bshift);
+                        advance(stage, phase, p.num_stages);
+                        continue;
+                    }
                     if (p.conv) {
                         const int tap = it / p.cin_blocks, cb = it - tap * p.cin_blocks;
                         const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
@@ -141,7 +166,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (lane == 0) {
             // ================= MMA issuer =================
-            const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n);
+            const uint32_t idesc = kWgrad ? umma_idesc_bf16_mn(kBlockM, p.block_n) : umma_idesc_bf16(kBlockM, p.block_n);
+            const uint32_t wg_lbo = 8192u, wg_sbo = 1024u;  // next 64 M/N columns (one TMA box) / next 8 K rows
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
@@ -152,7 +178,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!(ok = mbar_wait(&tmem_empty_bar[as], aphase ^ 1u, 0x200u))) break;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStageCols);
-                for (int it = 0; it < p.k_iters; ++it) {
+                int n_it = p.k_iters;
+                if (kWgrad) {
+                    const int it0 = (st / tiles_mn) * p.k_iters_split;
+                    n_it = min(p.k_iters, it0 + p.k_iters_split) - it0;
+                }
+                for (int it = 0; it < n_it; ++it) {
                     if (!(ok = mbar_wait(&full_bar[stage], phase, 0x300u))) break;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kStageBytesA) + (uint32_t)p.dbg_shift * 128u;
@@ -160,8 +191,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * stage_bytes_b);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32) | a_bo, umma_desc_sw128(b_addr + k * 32), idesc,
-                                  (uint32_t)((it | k) != 0));
+                        if (kWgrad)  // 16 K rows of 128 B per instruction
+                            umma_bf16(d_tmem, umma_desc_sw128_mn(a_addr + k * 2048, wg_lbo, wg_sbo),
+                                      umma_desc_sw128_mn(b_addr + k * 2048, wg_lbo, wg_sbo), idesc, (uint32_t)((it | k) != 0));
+                        else
+                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32) | a_bo, umma_desc_sw128(b_addr + k * 32), idesc,
+                                      (uint32_t)((it | k) != 0));
                     }
                     if (CS > 1) umma_commit_mc(&empty_bar[stage], cmask);  // the slot is refilled by every CTA of the cluster
                     else umma_commit(&empty_bar[stage]);
@@ -185,7 +220,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int local = 0;
         bool ok = true;
         for (int st = cluster_id; st < num_super && ok; st += num_clusters, ++local) {
-            const int m_tile = (st / p.num_n_tiles) * CS + cta_rank, n_tile = st % p.num_n_tiles;
+            const int split = kWgrad ? st / tiles_mn : 0, sm = kWgrad ? st - split * tiles_mn : st;
+            const int m_tile = (sm / n_cols) * CS + cta_rank, col = sm % n_cols;
+            const int tap = kWgrad ? col / p.num_n_tiles : 0, n_tile = kWgrad ? col - tap * p.num_n_tiles : col;
             const int m0 = m_tile * kBlockM, n0 = n_tile * p.block_n;
             const int as = local & 1;
             const uint32_t aphase = (uint32_t)(local >> 1) & 1u;
@@ -294,6 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // ---- store (+ statistics of the stored values)
                 if (p.out_f32) {
                     float* op = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ld_out + nb;
+                    if (kWgrad) op += (size_t)split * p.split_stride + (size_t)tap * p.N;
                     if (full && (p.ld_out & 3) == 0) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
@@ -533,7 +571,7 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        VPT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int num_super = ((p.num_m_tiles + cs - 1) / cs) * p.num_n_tiles;
@@ -554,7 +592,7 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     if (max_clusters[cs] == 0) {
         int n = 0;
         cfg.gridDim = dim3(num_sms() / cs * cs);
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel, &cfg);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<false>, &cfg);
         if (e != cudaSuccess || n <= 0) {
             (void)cudaGetLastError();
             n = num_sms() / cs;
@@ -564,6 +602,132 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     int clusters = max_clusters[cs];
     if (clusters > num_super) clusters = num_super;
     cfg.gridDim = dim3(clusters * cs);
-    VPT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, tmA, tmB, p));
+    VPT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, tmA, tmB, p));
+    return VPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight gradients: dW[m][tap*N + n] = sum_k a[k][m] * b[k + shift[tap]][n]   (K = pixels / tokens, split over CTAs)
+// ------------------------------------------------------------------------------------------------------
+namespace vpt {
+
+struct WgradPlan {
+    int block_n, n_tiles, m_tiles, k_iters, splits, k_iters_split;
+};
+
+static WgradPlan wgrad_plan(int M, int N, int ntaps, long long R) {
+    WgradPlan w;
+    w.block_n = N >= 256 ? 256 : (N + 63) / 64 * 64;  // whole 64-column TMA boxes
+    w.n_tiles = (N + w.block_n - 1) / w.block_n;
+    w.m_tiles = (M + kBlockM - 1) / kBlockM;
+    w.k_iters = (int)((R + kBlockK - 1) / kBlockK);
+    const int tiles = w.m_tiles * w.n_tiles * ntaps;
+    int splits = (2 * num_sms() + tiles - 1) / tiles;  // ~2 work items per SM
+    const int max_splits = w.k_iters / 8 > 0 ? w.k_iters / 8 : 1;  // at least 8 K iterations per item
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    w.k_iters_split = (w.k_iters + splits - 1) / splits;
+    w.splits = (w.k_iters + w.k_iters_split - 1) / w.k_iters_split;  // every split owns >= 1 iteration
+    return w;
+}
+
+// out[i] = sum_s part[s][i] in a fixed order; 4 floats per thread
+__global__ void __launch_bounds__(256) sum_splits_kernel(const float4* __restrict__ part, float4* __restrict__ out, long long n4, int splits) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = __ldg(part + i);
+        for (int s = 1; s < splits; ++s) {
+            const float4 b = __ldg(part + (long long)s * n4 + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
+    }
+}
+
+}  // namespace vpt
+
+extern "C" int64_t vpt_wgrad_workspace_bytes(int32_t M, int32_t N, int32_t ntaps, int64_t R) {
+    if (M <= 0 || N <= 0 || ntaps <= 0 || R <= 0) return 0;
+    const vpt::WgradPlan w = vpt::wgrad_plan(M, N, ntaps, R);
+    return w.splits > 1 ? (int64_t)w.splits * M * N * ntaps * 4 : 0;
+}
+
+extern "C" int vpt_wgrad_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t M, int32_t N, int64_t R, const int32_t* shifts,
+                              int32_t ntaps, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(a && b && out && shifts, "vpt_wgrad_bf16: null operand");
+    VPT_CHECK(M > 0 && N > 0 && R > 0 && ntaps >= 1 && ntaps <= 9, "vpt_wgrad_bf16: bad shape M=%d N=%d R=%lld ntaps=%d", M, N, (long long)R, ntaps);
+    VPT_CHECK(M % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= M && ldb >= N,
+              "vpt_wgrad_bf16: M, N and the row strides must be multiples of 8 (M=%d N=%d lda=%lld ldb=%lld)", M, N, (long long)lda, (long long)ldb);
+    VPT_CHECK(R < 2147483647LL - 4096, "vpt_wgrad_bf16: too many rows for 32-bit TMA coordinates");
+    VPT_CHECK(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)out & 15) == 0, "vpt_wgrad_bf16: pointers must be 16-byte aligned");
+    const WgradPlan w = wgrad_plan(M, N, ntaps, R);
+    const long long out_elems = (long long)M * N * ntaps;
+    VPT_CHECK(w.splits == 1 || (workspace && workspace_bytes >= (int64_t)w.splits * out_elems * 4),
+              "vpt_wgrad_bf16: workspace too small (%lld bytes, need %lld)", (long long)workspace_bytes, (long long)w.splits * out_elems * 4);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = (int)R;
+    p.block_n = w.block_n; p.num_n_tiles = w.n_tiles; p.num_m_tiles = w.m_tiles;
+    p.k_iters = w.k_iters; p.k_splits = w.splits; p.k_iters_split = w.k_iters_split;
+    p.ntaps = ntaps;
+    for (int i = 0; i < ntaps; ++i) p.tap_shift[i] = shifts[i];
+    p.cluster = 1;
+    p.px_per_frame = 1; p.W = 1; p.H = 1; p.rows_per_group = 1;
+    p.out_scale = 1.f;
+    p.out = w.splits > 1 ? workspace : (void*)out;
+    p.out_f32 = 1;
+    p.ld_out = (long long)N * ntaps;
+    p.split_stride = out_elems;
+    CUtensorMap tmA, tmB;
+    {   // MN-major operands: the tensor map's inner dimension is the operand's M (N) index, its rows are K
+        cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)R};
+        cuuint64_t strides[1] = {(cuuint64_t)lda * 2};
+        cuuint32_t box[2] = {64, 64};
+        int r = make_tmap_bf16(&tmA, a, 2, dims, strides, box);
+        if (r) return r;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)R};
+        cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
+        cuuint32_t box[2] = {64, 64};
+        int r = make_tmap_bf16(&tmB, b, 2, dims, strides, box);
+        if (r) return r;
+    }
+    const uint32_t stage_bytes = kStageBytesA + (uint32_t)p.block_n * kBlockK * 2;
+    int stages = (int)(200 * 1024 / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    p.num_stages = stages;
+    const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + (2 * kMaxStages + 4) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VPT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int items = w.m_tiles * w.n_tiles * ntaps * w.splits;
+    const int grid = items < num_sms() ? items : num_sms();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VPT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA, tmB, p));
+    if (w.splits > 1) {
+        const long long n4 = out_elems / 4;
+        long long blocks = (n4 + 255) / 256;
+        if (blocks > 4096) blocks = 4096;
+        sum_splits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(workspace),
+                                                                              reinterpret_cast<float4*>(out), n4, w.splits);
+        VPT_LAUNCH_CHECK();
+    }
     return VPT_OK;
 }

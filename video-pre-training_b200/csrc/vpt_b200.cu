@@ -28,6 +28,9 @@ void set_error(const char* fmt, ...) {
 #include "heads.cuh"
 #include "adam.cuh"
 #include "resize.cuh"
+#include "backward.cuh"
+#include "attention_bwd.cuh"
+#include "firstconv_bwd.cuh"
 
 extern "C" const char* vpt_last_error(void) { return vpt::g_err; }
 extern "C" int vpt_abi_version(void) { return VPT_ABI_VERSION; }

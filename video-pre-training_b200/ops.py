@@ -271,33 +271,25 @@ def add_zp(a, b, H, W, out=None):
     return out, stats_finalize(part, F_, P, H * W * Cc)
 
 
-def transpose(x):
-    """bf16 [R][C] -> [C][ld], ld = R rounded up to 8 (zero tail): the K-major operand layout of `wgrad`."""
-    _cuda(x)
-    R, Cc = x.shape
-    ld = (R + 7) // 8 * 8
-    out = torch.empty((Cc, ld), dtype=BF16, device=x.device)
-    nat.check(nat.lib().vpt_transpose_bf16(_p(x), _p(out), R, Cc, x.stride(0), ld, _stream()), "vpt_transpose_bf16")
-    _count()
-    return out
-
-
-def wgrad(aT, bT, R, shifts=(0,), out=None):
-    """fp32 out[m][tap*N + n] = sum_k aT[m][k] * bT[n][k + shifts[tap]] over k in [0, R) (out-of-range terms are zero)."""
-    _cuda(aT, bT)
-    M, N, ld = aT.shape[0], bT.shape[0], aT.shape[1]
-    assert bT.shape[1] == ld and aT.is_contiguous() and bT.is_contiguous()
+def wgrad(a, b, shifts=(0,), out=None):
+    """fp32 out[m][tap*N + n] = sum_k a[k][m] * b[k + shifts[tap]][n]: a bf16 [R][M] = output gradient, b bf16 [R][N] = layer input
+    (row strides allowed; rows outside [0, R) count as zero)."""
+    _cuda(a, b)
+    R, M = a.shape
+    N = b.shape[1]
+    assert b.shape[0] == R and a.stride(1) == 1 and b.stride(1) == 1
     nt = len(shifts)
     if out is None:
-        out = torch.empty((M, nt * N), dtype=F32, device=aT.device)
+        out = torch.empty((M, nt * N), dtype=F32, device=a.device)
     ws_bytes = nat.lib().vpt_wgrad_workspace_bytes(M, N, nt, R)
-    ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=F32, device=aT.device)
+    ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=F32, device=a.device)
     sh = (C.c_int32 * nt)(*[int(s) for s in shifts])
     prof = GEMM_PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    nat.check(nat.lib().vpt_wgrad_bf16(_p(aT), _p(bT), M, N, R, ld, sh, nt, _p(out), _p(ws), ws_bytes, _stream()), "vpt_wgrad_bf16")
+    nat.check(nat.lib().vpt_wgrad_bf16(_p(a), a.stride(0), _p(b), b.stride(0), M, N, R, sh, nt, _p(out), _p(ws), ws_bytes, _stream()),
+              "vpt_wgrad_bf16")
     if prof is not None:
         e1.record()
         prof.append((e0, e1, 2.0 * M * N * nt * R, "wgrad", (M, nt * N, R)))
@@ -373,8 +365,7 @@ def attention_bwd(Q, Kf, Vf, R, b_nd, first_u8, smask, dO, out, B, t, maxlen, he
     if not causal:
         raise NotImplementedError("attention_bwd: only the causal policy attention is trained")
     nbasis = b_nd.shape[0]
-    T = maxlen + t
-    ws = torch.empty((2, B * heads, t, T), dtype=F32, device=Q.device)  # P and dS
+    ws = torch.empty((2, B * heads, t, maxlen), dtype=F32, device=Q.device)  # P and dS by relative distance d
     db = torch.empty((nbasis, maxlen), dtype=F32, device=Q.device)
     nat.check(nat.lib().vpt_attention_bwd(_p(Q), _p(Kf), _p(Vf), _p(R), R.stride(-2), _p(b_nd), _p(first_u8), first_u8.stride(0), _p(smask),
                                           _p(dO), _p(out), out.stride(0), _p(db), _p(ws), B, t, maxlen, heads, nbasis, _stream()),

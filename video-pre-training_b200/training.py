@@ -125,9 +125,8 @@ class BCTrainer:
 
     @staticmethod
     def _wgrad_linear(dz, u, weight_param=None, rows_out=None):
-        """dW [out][in] = dz^T u via the transposed-operand GEMM; accumulated into `weight_param.grad` when given."""
-        R = dz.shape[0]
-        dW = ops.wgrad(ops.transpose(dz), ops.transpose(u), R)
+        """dW [out][in] = dz^T u (tcgen05 GEMM over the token dimension); accumulated into `weight_param.grad` when given."""
+        dW = ops.wgrad(dz, u)
         if rows_out is not None:
             dW = dW[:rows_out]
         if weight_param is not None:
@@ -154,7 +153,7 @@ class BCTrainer:
         du, _ = ops.conv3x3_zp(dz, W_rot, H, W, relu=0, want_stats=False)
         u, _ = ops.affine_norm_zp(x, mr, g32, bet.detach().float().contiguous())
         shifts = [(ky - 1) * (W + 1) + (kx - 1) for ky in range(3) for kx in range(3)]
-        dWk = ops.wgrad(ops.transpose(dz.view(R, Cout)), ops.transpose(u.view(R, Cin)), R, shifts)  # [Cout][tap][Cin]
+        dWk = ops.wgrad(dz.view(R, Cout), u.view(R, Cin), shifts)  # [Cout][tap][Cin]
         del u
         _acc(P[names + ".layer.weight"], dWk.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2))
         ident = lambda v: v
@@ -205,8 +204,7 @@ class BCTrainer:
             ops.softmax_bwd(pd[name].reshape(N, n), idx, scale, dlog, c0)
         loss = -logp.sum() / N
         # ---------------- heads ----------------
-        dlogT = ops.transpose(dlog)
-        dWh = ops.wgrad(dlogT, ops.transpose(lat_bf16), N)[: self.ntot]
+        dWh = ops.wgrad(dlog, lat_bf16)[: self.ntot]
         dbh = ops.col_sums(dlog)[1]
         for name in pol.head_specs:
             c0, width = hp["cols"][name]
@@ -215,7 +213,7 @@ class BCTrainer:
             _acc(lin.bias, dbh[c0:c0 + width])
         dlat = self._gemm(dlog, wts["heads_t"], h)
         self._dbg("latent", dlat)
-        del dlog, dlogT
+        del dlog
         # ---------------- final_ln (plain norm) + lastlayer ----------------
         ident = lambda v: v
         fg = P["final_ln.weight"]
