@@ -189,19 +189,26 @@ def test_bc_step_matches_emulated_step_and_oracle_direction():
     loss_o = -O.logprob(pd, actions).mean()
     loss_o.backward()
     assert abs(loss.item() - loss_o.item()) < 1e-2 * abs(loss_o.item())
-    worst = 0.0
+    errs, coss = {}, {}
     for n, p in pol.named_parameters():
         if n.startswith("value_head"):
             assert p.grad is None
             continue
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
-        e = rel(p.grad, grads_e[n])
-        worst = max(worst, e)
-        assert e < 0.15, (n, e)
+        errs[n] = rel(p.grad, grads_e[n])
         g_o = leaf[n].grad
-        cos = ((p.grad.cpu() * g_o).sum() / (p.grad.cpu().norm() * g_o.norm())).item()
-        assert cos > 0.8, (n, cos)
-    print("worst rel-L2 vs emulated step", worst)
+        coss[n] = ((p.grad.cpu() * g_o).sum() / (p.grad.cpu().norm() * g_o.norm())).item()
+    print("rel-L2 vs emulated step:", " ".join(f"{e:.3f}" for e in errs.values()))
+    print("cosine vs oracle autograd:", " ".join(f"{c:.3f}" for c in coss.values()))
+    # Two bf16 forwards with different summation orders decorrelate by ~1 % after a few layers, and every ReLU / max-pool mask
+    # between the loss and a parameter turns that into ~10 % gradient noise (tests/test_training.py), so only the parameters
+    # right below the loss can be compared tightly; for the rest the measure is the direction against the exact gradient
+    # (measured: cosine 0.93-0.96 in stack 0, > 0.98 in the transformer, 1.000 at the heads).
+    for n, e in errs.items():
+        top = n.startswith("pi_head") or n.startswith("net.final_ln")
+        assert e < (0.05 if top else 0.6), (n, e)
+    for n, c in coss.items():
+        assert c > 0.85, (n, c)
 
 
 def test_bc_training_reduces_the_loss():
