@@ -228,3 +228,26 @@ def test_bc_training_reduces_the_loss():
         losses.append(loss.item())
     nat.device_check()
     assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.5, losses
+
+
+def test_bc_step_at_3x_width_shapes():
+    """BASELINE configs[3] layer shapes (3x: 192/384/384 channels, hidsize 3072, 24 heads, 128-frame memory, 128x128 frames) on
+    a short clip: every backward kernel runs at its production shape, gradients are finite and Adam steps lower the loss."""
+    torch.manual_seed(0)
+    pol = vpt_b200.MinecraftAgentPolicy(vpt_b200.minecraft_action_space(), vpt_b200.policy_kwargs("3x"), vpt_b200.PI_HEAD_KWARGS).to(DEV)
+    g = torch.Generator().manual_seed(7)
+    B, T = 2, 8
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, generator=g).to(DEV)
+    first = torch.zeros(B, T, dtype=torch.bool, device=DEV)
+    actions = {"camera": torch.randint(0, 121, (B, T, 1), generator=g).to(DEV), "buttons": torch.randint(0, 8641, (B, T, 1), generator=g).to(DEV)}
+    tr = BCTrainer(pol)
+    opt = FlatAdamDP([p for n, p in pol.named_parameters() if not n.startswith("value_head")], lr=1e-4)
+    state, losses = pol.initial_state(B), []
+    for _ in range(4):
+        opt.zero_grad()
+        loss, state = tr.loss_and_grad(img, first, state, actions)  # the KV memory is carried (and detached) across steps
+        assert torch.isfinite(opt.flat_g).all()
+        opt.step()
+        losses.append(loss.item())
+    nat.device_check()
+    assert losses[-1] < losses[0], losses

@@ -13,7 +13,7 @@ parameter changes) they are re-laid-out for the kernels (`_Prepared`): conv weig
 the input GroupNorm gamma folded in plus the 9 border-class fold tables, linear weights with LayerNorm folded, the
 `dense` columns permuted from C,H,W to H,W,C order.
 
-Inference only (the kernels have no backward yet): forward runs under no_grad and returns detached tensors.
+`forward` runs under no_grad and returns detached tensors; the BC step has its own hand-written backward (training.py).
 There is no CPU path: CPU tensors raise.
 """
 import math
