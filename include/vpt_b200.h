@@ -245,18 +245,26 @@ int64_t vpt_wgrad_workspace_bytes(int32_t M, int32_t N, int32_t ntaps, int64_t R
  *   vpt_col_sums       out fp32 [2][C] = (sum_rows du*n, sum_rows du) = (d gamma, d beta); x == NULL: row 1 only (bias gradients);
  *                      workspace [vpt_col_sums_parts()][2][C] floats
  *   vpt_norm_bwd_apply dx = rstd * (gamma*du - ms.x - n*ms.y) [+ add]; zpC > 0: every group is a ZP frame [(zpH+1)(zpW+1)][zpC]
- *                      and its pad row / column is written as zero                          lib/util.py:44-63 (norm placement) */
+ *                      and its pad row / column is written as zero; relu_x != 0: x is a ReLU output, dx is zeroed where x == 0
+ *                      (the ReLU backward of the producer, fused)                          lib/util.py:44-63 (norm placement) */
 int vpt_group_sums(const void* du, const void* x, const float* mr, const float* gamma, float* part, float* ms, int64_t rows, int32_t C,
                    int32_t rows_per_group, double count, void* stream);
 int vpt_group_sums_parts(int32_t rows_per_group, int32_t C);
 int vpt_col_sums(const void* du, int64_t ld_du, const void* x, const float* mr, int64_t rows, int32_t C, int32_t rows_per_group, float* out,
                  float* workspace, void* stream);
 int vpt_col_sums_parts(int64_t rows, int32_t C);
+/* vpt_col_sums + vpt_group_sums in ONE pass over (du, x) for groups of many rows (GroupNorm frames): the per-channel partials of a
+ * slab that lies inside one group also give that group's sums.  out fp32 [2][C], ms fp32 [G][2]; workspace: vpt_norm_sums_workspace()
+ * floats. */
+int vpt_norm_sums(const void* du, const void* x, const float* mr, const float* gamma, int64_t rows, int32_t C, int32_t rows_per_group,
+                  double count, float* out, float* ms, float* workspace, void* stream);
+int64_t vpt_norm_sums_workspace(int64_t rows, int32_t C, int32_t rows_per_group);
 int vpt_norm_bwd_apply(const void* du, const void* x, const float* mr, const float* gamma, const float* ms, const void* add, void* dx,
-                       int64_t rows, int32_t C, int32_t rows_per_group, int32_t zpH, int32_t zpW, int32_t zpC, void* stream);
-/* Backward of ReLU -> max_pool2d(3, 2, 1) on ZP tensors (H, W = pool input size): dx[F][H+1][W+1][C] from dy, y [F][H/2+1][W/2+1][C]
- * and the post-ReLU pool input x; the first maximum in window scan order takes the gradient     lib/impala_cnn.py:115-117 */
-int vpt_maxpool3s2_bwd(const void* dy, const void* x, const void* y, void* dx, int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
+                       int64_t rows, int32_t C, int32_t rows_per_group, int32_t zpH, int32_t zpW, int32_t zpC, int32_t relu_x, void* stream);
+/* Backward of ReLU -> max_pool2d(3, 2, 1) on ZP tensors (H, W = pool input size): dx[F][H+1][W+1][C] from dy [F][H/2+1][W/2+1][C] and the
+ * post-ReLU pool input x; the first maximum in window scan order takes the gradient (torch semantics), windows whose maximum is 0
+ * pass none.  workspace: F*(H/2)*(W/2)*C bytes (arg-max position per pooled element)             lib/impala_cnn.py:115-117 */
+int vpt_maxpool3s2_bwd(const void* dy, const void* x, void* dx, void* workspace, int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
 /* Weight / bias gradient of vpt_firstconv_pool (recomputes the pre-pool map): dW fp32 [C0][27] (same (ky,kx,c) order and /255 scale
  * as w), db [C0]; dy bf16 ZP [F][H/2+1][W/2+1][C0]; workspace [vpt_firstconv_bwd_parts()][C0][28] floats */
 int vpt_firstconv_bwd(const uint8_t* img, const float* w, const float* bias, const void* dy, float* dW, float* db, float* workspace, int64_t F,

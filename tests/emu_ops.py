@@ -290,7 +290,11 @@ def col_sums(du, x=None, mr=None, rows_per_group=1):
     return out
 
 
-def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None):
+def norm_sums(du, x, mr, gamma, rows_per_group, count):
+    return col_sums(du, x, mr, rows_per_group), group_sums(du, x, mr, gamma, rows_per_group, count)
+
+
+def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None, relu_x=False):
     """dx = rstd * (gamma*du - m1 - n*m2) [+ add] on [rows][C]; with zp = (H, W, Cch) every group is a ZP frame
     [(H+1)(W+1)][Cch] (flattened over rows_per_group rows of C) whose pad row / column is written as zero."""
     Cc = x.shape[-1]
@@ -300,6 +304,8 @@ def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None):
     if add is not None:
         dx = dx + add.float().reshape(-1, Cc)
     dx = dx.to(BF16)
+    if relu_x:
+        dx = torch.where(x.float().reshape(-1, Cc) > 0, dx, torch.zeros((), dtype=BF16))
     if zp is not None:
         H, W, Cch = zp
         e = torch.arange(rows_per_group * Cc) // Cch          # pixel row inside the frame
@@ -308,7 +314,7 @@ def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None):
     return dx.reshape(x.shape)
 
 
-def maxpool3s2_bwd(dy, x, y):
+def maxpool3s2_bwd(dy, x):
     """Gradient of max_pool2d(3,2,1) (+ the ReLU in front of it: x is post-ReLU) on ZP tensors; first maximum wins ties."""
     xi = from_zp(x).float().permute(0, 3, 1, 2).requires_grad_(True)
     yo = F.max_pool2d(xi, 3, 2, 1)

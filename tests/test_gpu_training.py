@@ -90,9 +90,16 @@ def test_norm_backward_passes(rows, C, rpg, zp):
     cs = ops.col_sums(du.to(DEV), x.to(DEV), mr.to(DEV), rpg)
     assert rel(cs, cs_e) < 1e-5
     assert rel(ops.col_sums(du.to(DEV))[1], cs_e[1]) < 1e-5
+    if rpg > 1:
+        cs2, ms2 = ops.norm_sums(du.to(DEV), x.to(DEV), mr.to(DEV), gamma.to(DEV), rpg, count)
+        assert rel(cs2, cs_e) < 1e-5 and torch.allclose(ms2.cpu(), ms_e, rtol=2e-4, atol=2e-6)
     dx_e = E.norm_bwd_apply(du, x, mr, gamma, ms_e, rpg, zp=zp, add=add)
     dx = ops.norm_bwd_apply(du.to(DEV), x.to(DEV), mr.to(DEV), gamma.to(DEV), ms_e.to(DEV), rpg, zp=zp, add=add.to(DEV))
     assert rel(dx, dx_e) < 4e-3 and (dx.float().cpu() - dx_e.float()).abs().max() <= 2 ** -7 * dx_e.float().abs().max()
+    xr = x.float().relu().to(BF16)  # a ReLU output as the norm input: its backward is fused into the apply pass
+    dxr_e = E.norm_bwd_apply(du, xr, mr, gamma, ms_e, rpg, zp=zp, relu_x=True)
+    dxr = ops.norm_bwd_apply(du.to(DEV), xr.to(DEV), mr.to(DEV), gamma.to(DEV), ms_e.to(DEV), rpg, zp=zp, relu_x=True)
+    assert rel(dxr, dxr_e) < 4e-3 and ((dxr.cpu() == 0) | (xr > 0)).all()
     if zp is not None:
         d4 = dx.cpu().reshape(G, zp[0] + 1, zp[1] + 1, -1)
         assert (d4[:, -1] == 0).all() and (d4[:, :, -1] == 0).all()
@@ -102,10 +109,9 @@ def test_maxpool_backward_with_ties():
     g = torch.Generator().manual_seed(3)
     # coarse values -> many exact ties inside windows; ~half the inputs are zero (post-ReLU)
     x = E.to_zp((torch.randint(-3, 4, (3, 16, 16, 64), generator=g).float().relu() * 0.5).to(BF16))
-    y, _ = E.maxpool3s2(x)
     dy = zp_rand(3, 8, 8, 64, g)
-    ref = E.maxpool3s2_bwd(dy, x, y)
-    out = ops.maxpool3s2_bwd(dy.to(DEV), x.to(DEV), y.to(DEV))
+    ref = E.maxpool3s2_bwd(dy, x)
+    out = ops.maxpool3s2_bwd(dy.to(DEV), x.to(DEV))
     assert torch.equal(out.cpu(), ref)
 
 

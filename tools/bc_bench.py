@@ -97,7 +97,7 @@ if a.profile and rank == 0:
 if a.ops and rank == 0:
     import collections
     names = ["gemm", "conv3x3_zp", "wgrad", "firstconv_pool", "maxpool3s2", "affine_norm", "affine_norm_zp", "add_zp", "attention", "relu_mask",
-             "group_sums", "col_sums", "norm_bwd_apply", "maxpool3s2_bwd", "firstconv_bwd", "attention_bwd", "softmax_bwd", "copy_rows",
+             "group_sums", "col_sums", "norm_sums", "norm_bwd_apply", "maxpool3s2_bwd", "firstconv_bwd", "attention_bwd", "softmax_bwd", "copy_rows",
              "log_softmax", "gather_logprob", "stats_finalize"]
     rec = []
 

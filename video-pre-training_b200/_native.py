@@ -108,8 +108,10 @@ SIGNATURES = {
     "vpt_group_sums_parts": (_I, [_I, _I]),
     "vpt_col_sums": (_I, [_P, _L, _P, _P, _L, _I, _I, _P, _P, _P]),
     "vpt_col_sums_parts": (_I, [_L, _I]),
-    "vpt_norm_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
-    "vpt_maxpool3s2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "vpt_norm_sums": (_I, [_P, _P, _P, _P, _L, _I, _I, _D, _P, _P, _P, _P]),
+    "vpt_norm_sums_workspace": (_L, [_L, _I, _I]),
+    "vpt_norm_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P]),
+    "vpt_maxpool3s2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),  # dy, x, dx, workspace
     "vpt_firstconv_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     "vpt_firstconv_bwd_parts": (_I, [_L, _I, _I]),
     "vpt_attention_bwd": (_I, [_P, _P, _P, _P, _L, _P, _P, _L, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _P]),

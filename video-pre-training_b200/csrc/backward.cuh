@@ -111,14 +111,27 @@ __global__ void sums_finalize_kernel(const float2* __restrict__ part, float2* __
 // grid = (ceil(C8/32), S row slabs); partials [S][2][C] summed in a fixed order by col_sums_finalize_kernel
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __restrict__ du, long long ld_du, const __nv_bfloat16* __restrict__ x,
-                                                         const float2* __restrict__ mr, float* __restrict__ ws, long long rows, int C,
-                                                         int rows_per_group, long long rows_per_slab) {
+                                                         const float2* __restrict__ mr, const float* __restrict__ gamma, float* __restrict__ ws,
+                                                         float2* __restrict__ gpart, long long rows, int C, int rows_per_group, int slabs_per_group,
+                                                         long long rows_per_slab) {
     __shared__ float red[8][32][17];
     const int vl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int cv = blockIdx.x * 32 + vl;
     const bool active = cv * 8 < C;
-    const long long r_begin = (long long)blockIdx.y * rows_per_slab;
-    const long long r_end = min(rows, r_begin + rows_per_slab);
+    // slabs_per_group > 0: every slab lies inside one statistics group (its (mean, rstd) is loaded once, and the block can also
+    // emit the group's  sum gamma*du  /  sum gamma*du*n  partials -- the "group sums" of the norm backward -- from its column sums)
+    long long r_begin, r_end;
+    float2 st = make_float2(0.f, 1.f);
+    if (slabs_per_group > 0) {
+        const long long g = blockIdx.y / slabs_per_group;
+        const int k = blockIdx.y - (int)g * slabs_per_group;
+        r_begin = g * rows_per_group + k * rows_per_slab;
+        r_end = min((g + 1) * rows_per_group, r_begin + rows_per_slab);
+        if (x != nullptr) st = __ldg(mr + g);
+    } else {
+        r_begin = (long long)blockIdx.y * rows_per_slab;
+        r_end = min(rows, r_begin + rows_per_slab);
+    }
     float a0[8], a1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __re
             if (x != nullptr) {
                 float xv[8];
                 unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * (long long)C + cv * 8)), xv);
-                const float2 st = __ldg(mr + r / rows_per_group);
+                if (slabs_per_group == 0) st = __ldg(mr + (rows_per_group == 1 ? r : r / rows_per_group));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a0[j] = fmaf(d[j], (xv[j] - st.x) * st.y, a0[j]);
             }
@@ -144,6 +157,7 @@ __global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __re
     }
     __syncthreads();
     // 256 threads: (vector lane, value 0..15) pairs of this block -> 512 outputs, two per thread
+    float g1 = 0.f, g2 = 0.f;
     for (int o = threadIdx.x; o < 32 * 16; o += 256) {
         const int v = o >> 4, k = o & 15;
         const int c = (blockIdx.x * 32 + v) * 8 + (k & 7);
@@ -152,15 +166,34 @@ __global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __re
 #pragma unroll
         for (int q = 0; q < 8; ++q) s += red[q][v][k];
         ws[((long long)blockIdx.y * 2 + (k >> 3)) * C + c] = s;
+        if (gpart != nullptr) {
+            const float gs = __ldg(gamma + c) * s;
+            if (k >> 3) g1 += gs;  // sum gamma * du
+            else g2 += gs;         // sum gamma * du * n
+        }
+    }
+    if (gpart != nullptr) {
+        const float2 r = block_sum2(g1, g2);
+        if (threadIdx.x == 0) gpart[(long long)blockIdx.y * gridDim.x + blockIdx.x] = r;
     }
 }
 
+// out[i] = sum_s ws[s][i], i over 2*C; block = 32 outputs x 8 slab lanes, fixed-order combination
 __global__ void __launch_bounds__(256) col_sums_finalize_kernel(const float* __restrict__ ws, float* __restrict__ out, int n, int S) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i over 2*C
-    if (i >= n) return;
+    __shared__ double red[8][32];
+    const int l = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + l;
     double a = 0.0;
-    for (int s = 0; s < S; ++s) a += (double)__ldg(ws + (long long)s * n + i);
-    out[i] = (float)a;
+    if (i < n)
+        for (int s = sl; s < S; s += 8) a += (double)__ldg(ws + (long long)s * n + i);
+    red[sl][l] = a;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][l];
+        out[i] = (float)t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -169,23 +202,25 @@ __global__ void __launch_bounds__(256) col_sums_finalize_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const uint4* __restrict__ du, const uint4* __restrict__ x, const float2* __restrict__ mr,
                                                                const float* __restrict__ gamma, const float2* __restrict__ ms,
-                                                               const uint4* __restrict__ add, uint4* __restrict__ dx, long long total, int C8,
-                                                               long long items_per_group, int zpH, int zpW, int zpC8) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long g = i / items_per_group;
+                                                               const uint4* __restrict__ add, uint4* __restrict__ dx, int C8, int items_per_group,
+                                                               int zpH, int zpW, int zpC8, int relu_x) {
+    // grid = (blocks per group, groups): no 64-bit index arithmetic in the loop
+    const long long g = blockIdx.y, base = g * items_per_group;
+    const float2 st = __ldg(mr + g), m = __ldg(ms + g);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items_per_group; i += gridDim.x * blockDim.x) {
         if (zpC8 > 0) {
-            const long long pix = (i - g * items_per_group) / zpC8;
-            const int py = (int)(pix / (zpW + 1)), px = (int)(pix - (long long)py * (zpW + 1));
+            const int pix = i / zpC8;
+            const int py = pix / (zpW + 1), px = pix - py * (zpW + 1);
             if (py >= zpH || px >= zpW) {
-                dx[i] = make_uint4(0, 0, 0, 0);
+                dx[base + i] = make_uint4(0, 0, 0, 0);
                 continue;
             }
         }
-        const int c = (int)(i % C8) * 8;
-        const float2 st = __ldg(mr + g), m = __ldg(ms + g);
+        const int c = (i % C8) * 8;
         float d[8], xv[8], ga[8];
-        unpack8(__ldg(du + i), d);
-        unpack8(__ldg(x + i), xv);
+        unpack8(__ldg(du + base + i), d);
+        const uint4 xr = __ldg(x + base + i);
+        unpack8(xr, xv);
         load8f(gamma + c, ga);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -194,28 +229,72 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const uint4* __rest
         }
         if (add != nullptr) {
             float a[8];
-            unpack8(__ldg(add + i), a);
+            unpack8(__ldg(add + base + i), a);
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[j] += a[j];
         }
-        dx[i] = pack8(d);
+        uint4 o = pack8(d);
+        if (relu_x) {  // x is itself a ReLU output: chain its backward (dx = 0 where x == 0) instead of a separate masking pass
+            o.x &= pos_mask2(xr.x); o.y &= pos_mask2(xr.y); o.z &= pos_mask2(xr.z); o.w &= pos_mask2(xr.w);
+        }
+        dx[base + i] = o;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// backward of ReLU -> max_pool2d(3, 2, 1) on ZP tensors; one thread per (input pixel, 8 channels); grid = (blocks, F).
-// The first maximum in window scan order wins ties (torch semantics); windows whose maximum is 0 pass no gradient
-// (their inputs are all <= 0 before the ReLU).
+// backward of ReLU -> max_pool2d(3, 2, 1) on ZP tensors, two streaming passes:
+//   1. per pooled pixel: which of the 9 window positions holds the FIRST maximum (torch tie semantics), one byte per channel
+//      (15 = no gradient: the maximum is 0, i.e. every input was <= 0 before the ReLU)
+//   2. per input pixel: sum dy over the (at most 4) windows whose arg-max byte names this pixel
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
-                                                               uint4* __restrict__ dx, int H, int W, int C8) {
+__global__ void __launch_bounds__(256) maxpool3s2_argmax_kernel(const uint4* __restrict__ x, uint2* __restrict__ idx, int H, int W, int C8) {
+    const int Ho = H >> 1, Wo = W >> 1, ip = W + 1;
+    const long long f = blockIdx.y;
+    const int items = Ho * Wo * C8;
+    const uint4* fx = x + f * (long long)(H + 1) * ip * C8;
+    uint2* fi = idx + f * (long long)items;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
+        const int c = i % C8, ox = (i / C8) % Wo, oy = i / (C8 * Wo);
+        float best[8];
+        uint32_t arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            best[j] = 0.f;  // inputs are >= 0: a window that never exceeds 0 passes no gradient
+            arg[j] = 15u;
+        }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int y = 2 * oy - 1 + dy;
+            if (y < 0 || y >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int xx = 2 * ox - 1 + dx;
+                if (xx < 0 || xx >= W) continue;
+                float v[8];
+                unpack8(__ldg(fx + ((long long)y * ip + xx) * C8 + c), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (v[j] > best[j]) {
+                        best[j] = v[j];
+                        arg[j] = (uint32_t)(dy * 3 + dx);
+                    }
+            }
+        }
+        uint2 o;
+        o.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+        o.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+        fi[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx, int H,
+                                                               int W, int C8) {
     const int Ho = H >> 1, Wo = W >> 1;
     const int ip = W + 1, op = Wo + 1;
     const long long f = blockIdx.y;
     const int items = (H + 1) * ip * C8;
-    const uint4* fx = x + f * (long long)items;
     uint4* fdx = dx + f * (long long)items;
-    const uint4* fy = y + f * (long long)(Ho + 1) * op * C8;
+    const uint2* fi = idx + f * (long long)Ho * Wo * C8;
     const uint4* fdy = dy + f * (long long)(Ho + 1) * op * C8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
         const int c = i % C8, ix = (i / C8) % ip, iy = i / (C8 * ip);
@@ -223,8 +302,6 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const uint4* __rest
             fdx[i] = make_uint4(0, 0, 0, 0);
             continue;
         }
-        const uint4 v4 = __ldg(fx + i);
-        const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -233,40 +310,17 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const uint4* __rest
             if (oy >= Ho) continue;
             for (int ox = ox0; ox <= ox1; ++ox) {
                 if (ox >= Wo) continue;
-                const uint4 m4 = __ldg(fy + ((long long)oy * op + ox) * C8 + c);
-                const uint32_t m[4] = {m4.x, m4.y, m4.z, m4.w};
-                // lanes where this input equals the (positive) window maximum
-                uint32_t hit[4];
-                bool any = false;
+                const uint32_t code = (uint32_t)((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));  // this pixel's position in the window
+                const uint2 a = __ldg(fi + ((long long)oy * Wo + ox) * C8 + c);
+                const uint32_t eq_lo = a.x ^ (code * 0x01010101u), eq_hi = a.y ^ (code * 0x01010101u);
+                if (((eq_lo - 0x01010101u) & ~eq_lo & 0x80808080u) == 0u && ((eq_hi - 0x01010101u) & ~eq_hi & 0x80808080u) == 0u)
+                    continue;  // no zero byte: none of the 8 channels selected this pixel
+                float g[8];
+                unpack8(__ldg(fdy + ((long long)oy * op + ox) * C8 + c), g);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t eq = ~(v[q] ^ m[q]);
-                    const uint32_t e = ((eq & 0xffffu) == 0xffffu ? 0xffffu : 0u) | ((eq >> 16) == 0xffffu ? 0xffff0000u : 0u);
-                    hit[q] = e & pos_mask2(m[q]);
-                    any |= hit[q] != 0u;
-                }
-                if (!any) continue;
-                // earlier positions of the window (row-major scan) holding the same value take the gradient instead
-                for (int wy = 2 * oy - 1; wy <= iy; ++wy) {
-                    if (wy < 0) continue;
-                    const int wx_end = (wy == iy) ? ix - 1 : min(2 * ox + 1, W - 1);
-                    for (int wx = max(2 * ox - 1, 0); wx <= wx_end; ++wx) {
-                        const uint4 e4 = __ldg(fx + ((long long)wy * ip + wx) * C8 + c);
-                        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t eq = ~(e[q] ^ m[q]);
-                            const uint32_t same = ((eq & 0xffffu) == 0xffffu ? 0xffffu : 0u) | ((eq >> 16) == 0xffffu ? 0xffff0000u : 0u);
-                            hit[q] &= ~same;
-                        }
-                    }
-                }
-                const uint4 g4 = __ldg(fdy + ((long long)oy * op + ox) * C8 + c);
-                const uint32_t g[4] = {g4.x & hit[0], g4.y & hit[1], g4.z & hit[2], g4.w & hit[3]};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    acc[2 * q] += bf16_lo(g[q]);
-                    acc[2 * q + 1] += bf16_hi(g[q]);
+                for (int j = 0; j < 4; ++j) {
+                    if (((eq_lo >> (8 * j)) & 0xffu) == 0u) acc[j] += g[j];
+                    if (((eq_hi >> (8 * j)) & 0xffu) == 0u) acc[4 + j] += g[4 + j];
                 }
             }
         }
@@ -363,6 +417,15 @@ static inline int col_sums_slabs(long long rows, int C) {
     if (S > 65535) S = 65535;
     return (int)S;
 }
+// slabs per statistics group of the fused (column + group sums) pass
+static inline int norm_sums_spg(long long groups, int rows_per_group, int C) {
+    const int colblocks = (C / 8 + 31) / 32;
+    long long spg = (4LL * 148 + colblocks * groups - 1) / (colblocks * groups);
+    const long long max_spg = (rows_per_group + 63) / 64;
+    if (spg > max_spg) spg = max_spg;
+    if (spg < 1) spg = 1;
+    return (int)spg;
+}
 }  // namespace vpt
 
 extern "C" int vpt_col_sums_parts(int64_t rows, int32_t C) { return vpt::col_sums_slabs(rows, C); }
@@ -376,37 +439,81 @@ extern "C" int vpt_col_sums(const void* du, int64_t ld_du, const void* x, const 
     const long long per = (rows + S - 1) / S;
     dim3 grid((C / 8 + 31) / 32, S);
     col_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(du), ld_du, reinterpret_cast<const __nv_bfloat16*>(x),
-                                                           reinterpret_cast<const float2*>(mr), workspace, rows, C,
-                                                           rows_per_group > 0 ? rows_per_group : 1, per);
+                                                           reinterpret_cast<const float2*>(mr), nullptr, workspace, nullptr, rows, C,
+                                                           rows_per_group > 0 ? rows_per_group : 1, 0, per);
     VPT_LAUNCH_CHECK();
-    col_sums_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, out, 2 * C, S);
+    col_sums_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(workspace, out, 2 * C, S);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}
+
+extern "C" int64_t vpt_norm_sums_workspace(int64_t rows, int32_t C, int32_t rows_per_group) {
+    if (rows <= 0 || C <= 0 || rows_per_group <= 0) return 0;
+    const long long G = rows / rows_per_group;
+    const long long S = G * vpt::norm_sums_spg(G, rows_per_group, C);
+    return S * 2 * C + S * ((C / 8 + 31) / 32) * 2;
+}
+
+extern "C" int vpt_norm_sums(const void* du, const void* x, const float* mr, const float* gamma, int64_t rows, int32_t C, int32_t rows_per_group,
+                             double count, float* out, float* ms, float* workspace, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(du && x && mr && gamma && out && ms && workspace, "vpt_norm_sums: null argument");
+    VPT_CHECK(rows > 0 && C > 0 && C % 8 == 0 && rows_per_group > 0 && rows % rows_per_group == 0 && count > 0,
+              "vpt_norm_sums: bad shape rows=%lld C=%d rows_per_group=%d", (long long)rows, C, rows_per_group);
+    const long long G = rows / rows_per_group;
+    const int spg = norm_sums_spg(G, rows_per_group, C);
+    const long long S = G * spg;
+    VPT_CHECK(S <= 65535, "vpt_norm_sums: too many groups (%lld) for one launch", (long long)G);
+    const int colblocks = (C / 8 + 31) / 32;
+    const long long per = (rows_per_group + spg - 1) / spg;
+    float* ws_cols = workspace;
+    float2* gpart = reinterpret_cast<float2*>(workspace + S * 2 * C);
+    dim3 grid(colblocks, (unsigned)S);
+    col_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(du), C, reinterpret_cast<const __nv_bfloat16*>(x),
+                                                           reinterpret_cast<const float2*>(mr), gamma, ws_cols, gpart, rows, C, rows_per_group, spg, per);
+    VPT_LAUNCH_CHECK();
+    col_sums_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(ws_cols, out, 2 * C, (int)S);
+    VPT_LAUNCH_CHECK();
+    sums_finalize_kernel<<<(unsigned)((G + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gpart, reinterpret_cast<float2*>(ms), G, spg * colblocks, 1.0 / count);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
 
 extern "C" int vpt_norm_bwd_apply(const void* du, const void* x, const float* mr, const float* gamma, const float* ms, const void* add, void* dx,
-                                  int64_t rows, int32_t C, int32_t rows_per_group, int32_t zpH, int32_t zpW, int32_t zpC, void* stream) {
+                                  int64_t rows, int32_t C, int32_t rows_per_group, int32_t zpH, int32_t zpW, int32_t zpC, int32_t relu_x, void* stream) {
     using namespace vpt;
     VPT_CHECK(du && x && mr && gamma && ms && dx, "vpt_norm_bwd_apply: null argument");
     VPT_CHECK(rows > 0 && C > 0 && C % 8 == 0 && rows_per_group > 0 && rows % rows_per_group == 0, "vpt_norm_bwd_apply: bad shape");
     VPT_CHECK(zpC == 0 || (zpC % 8 == 0 && (long long)(zpH + 1) * (zpW + 1) * zpC == (long long)rows_per_group * C),
               "vpt_norm_bwd_apply: ZP geometry (%d,%d,%d) does not match the group size", zpH, zpW, zpC);
-    const long long total = rows * (long long)C / 8, ipg = (long long)rows_per_group * C / 8;
-    norm_bwd_apply_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4*>(du), reinterpret_cast<const uint4*>(x), reinterpret_cast<const float2*>(mr), gamma,
-        reinterpret_cast<const float2*>(ms), reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), total, C / 8, ipg, zpH, zpW, zpC / 8);
-    VPT_LAUNCH_CHECK();
+    const long long G = rows / rows_per_group, ipg = (long long)rows_per_group * C / 8;
+    VPT_CHECK(ipg < 2147483647LL, "vpt_norm_bwd_apply: group too large");
+    const int P = parts_for(ipg * 4);  // ~256 items per block-iteration
+    for (long long g0 = 0; g0 < G; g0 += 65535) {
+        const long long gn = min((long long)65535, G - g0);
+        dim3 grid(P, (unsigned)gn);
+        norm_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(du) + g0 * ipg, reinterpret_cast<const uint4*>(x) + g0 * ipg, reinterpret_cast<const float2*>(mr) + g0, gamma,
+            reinterpret_cast<const float2*>(ms) + g0, add ? reinterpret_cast<const uint4*>(add) + g0 * ipg : nullptr,
+            reinterpret_cast<uint4*>(dx) + g0 * ipg, C / 8, (int)ipg, zpH, zpW, zpC / 8, relu_x);
+        VPT_LAUNCH_CHECK();
+    }
     return VPT_OK;
 }
 
-extern "C" int vpt_maxpool3s2_bwd(const void* dy, const void* x, const void* y, void* dx, int32_t F, int32_t H, int32_t W, int32_t C, void* stream) {
+extern "C" int vpt_maxpool3s2_bwd(const void* dy, const void* x, void* dx, void* workspace, int32_t F, int32_t H, int32_t W, int32_t C, void* stream) {
     using namespace vpt;
-    VPT_CHECK(dy && x && y && dx && F > 0 && F <= 65535, "vpt_maxpool3s2_bwd: bad arguments");
+    VPT_CHECK(dy && x && dx && workspace && F > 0 && F <= 65535, "vpt_maxpool3s2_bwd: bad arguments");
     VPT_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vpt_maxpool3s2_bwd: need even H, W and C %% 8 == 0");
+    VPT_CHECK(((uintptr_t)workspace & 7) == 0, "vpt_maxpool3s2_bwd: workspace must be 8-byte aligned");
+    const long long out_items = (long long)(H / 2) * (W / 2) * (C / 8);
+    dim3 g1(grid_for(out_items, 256, 64), F);
+    maxpool3s2_argmax_kernel<<<g1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint2*>(workspace), H, W, C / 8);
+    VPT_LAUNCH_CHECK();
     const long long items = (long long)(H + 1) * (W + 1) * (C / 8);
-    dim3 grid(grid_for(items, 256, 64), F);
-    maxpool3s2_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x),
-                                                                 reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(dx), H, W, C / 8);
+    dim3 g2(grid_for(items, 256, 64), F);
+    maxpool3s2_bwd_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(workspace),
+                                                              reinterpret_cast<uint4*>(dx), H, W, C / 8);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

@@ -617,7 +617,17 @@ struct WgradPlan {
 
 static WgradPlan wgrad_plan(int M, int N, int ntaps, long long R) {
     WgradPlan w;
-    w.block_n = N >= 256 ? 256 : (N + 63) / 64 * 64;  // whole 64-column TMA boxes
+    // whole 64-column TMA boxes; among 256 / 192 / 128 pick the width that pads N the least (N = 384 -> 2 x 192, not 256 + 128)
+    if (N <= 256) {
+        w.block_n = (N + 63) / 64 * 64;
+    } else {
+        int best = 256, best_pad = (N + 255) / 256 * 256 - N;
+        for (int bn = 192; bn >= 128; bn -= 64) {
+            const int pad = (N + bn - 1) / bn * bn - N;
+            if (pad < best_pad) { best = bn; best_pad = pad; }
+        }
+        w.block_n = best;
+    }
     w.n_tiles = (N + w.block_n - 1) / w.block_n;
     w.m_tiles = (M + kBlockM - 1) / kBlockM;
     w.k_iters = (int)((R + kBlockK - 1) / kBlockK);

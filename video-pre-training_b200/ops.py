@@ -323,25 +323,41 @@ def col_sums(du, x=None, mr=None, rows_per_group=1):
     return out
 
 
-def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None):
-    """dx = rstd * (gamma*du - m1 - n*m2) [+ add] (bf16 [rows][C]); zp = (H, W, Cch): groups are ZP frames, pads written as 0."""
+def norm_sums(du, x, mr, gamma, rows_per_group, count):
+    """(col_sums(du, x, mr), group_sums(du, x, mr, gamma)) in one pass over the data; for groups of many rows (GroupNorm frames)."""
+    _cuda(du, x, mr, gamma)
+    rows, Cc = x.shape
+    G = rows // rows_per_group
+    out = torch.empty((2, Cc), dtype=F32, device=x.device)
+    ms = torch.empty((G, 2), dtype=F32, device=x.device)
+    ws = torch.empty((nat.lib().vpt_norm_sums_workspace(rows, Cc, rows_per_group),), dtype=F32, device=x.device)
+    nat.check(nat.lib().vpt_norm_sums(_p(du), _p(x), _p(mr), _p(gamma), rows, Cc, rows_per_group, float(count), _p(out), _p(ms), _p(ws), _stream()),
+              "vpt_norm_sums")
+    _count(3)
+    return out, ms
+
+
+def norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=None, add=None, relu_x=False):
+    """dx = rstd * (gamma*du - m1 - n*m2) [+ add] (bf16 [rows][C]); zp = (H, W, Cch): groups are ZP frames, pads written as 0;
+    relu_x: x is a ReLU output and dx is zeroed where x == 0 (the producer's ReLU backward, fused)."""
     _cuda(du, x, mr, gamma, ms, add)
     rows, Cc = x.shape
     dx = torch.empty_like(x)
     H, W, Cch = zp if zp is not None else (0, 0, 0)
     nat.check(nat.lib().vpt_norm_bwd_apply(_p(du), _p(x), _p(mr), _p(gamma), _p(ms), _p(add), _p(dx), rows, Cc, rows_per_group, H, W, Cch,
-                                           _stream()), "vpt_norm_bwd_apply")
+                                           int(relu_x), _stream()), "vpt_norm_bwd_apply")
     _count()
     return dx
 
 
-def maxpool3s2_bwd(dy, x, y):
-    """Gradient of ReLU -> max_pool2d(3, 2, 1) on ZP tensors: dy, y [F,H/2+1,W/2+1,C], x (post-ReLU pool input) [F,H+1,W+1,C]."""
-    _cuda(dy, x, y)
+def maxpool3s2_bwd(dy, x):
+    """Gradient of ReLU -> max_pool2d(3, 2, 1) on ZP tensors: dy [F,H/2+1,W/2+1,C], x (post-ReLU pool input) [F,H+1,W+1,C]."""
+    _cuda(dy, x)
     F_, H, W, Cc = x.shape[0], x.shape[1] - 1, x.shape[2] - 1, x.shape[3]
     dx = torch.empty_like(x)
-    nat.check(nat.lib().vpt_maxpool3s2_bwd(_p(dy), _p(x), _p(y), _p(dx), F_, H, W, Cc, _stream()), "vpt_maxpool3s2_bwd")
-    _count()
+    ws = torch.empty((F_ * (H // 2) * (W // 2) * Cc,), dtype=torch.uint8, device=x.device)
+    nat.check(nat.lib().vpt_maxpool3s2_bwd(_p(dy), _p(x), _p(dx), _p(ws), F_, H, W, Cc, _stream()), "vpt_maxpool3s2_bwd")
+    _count(2)
     return dx
 
 

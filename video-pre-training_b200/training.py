@@ -134,16 +134,20 @@ class BCTrainer:
         return dW
 
     @staticmethod
-    def _norm_bwd(du, x, mr, gamma, rows_per_group, count, g_param, b_param, zp=None, add=None):
-        """Backward of n = (x - mean) * rstd, u = gamma * n + beta given du: accumulates dgamma / dbeta, returns dx (+ add)."""
-        cs = ops.col_sums(du, x, mr, rows_per_group)
+    def _norm_bwd(du, x, mr, gamma, rows_per_group, count, g_param, b_param, zp=None, add=None, relu_x=False):
+        """Backward of n = (x - mean) * rstd, u = gamma * n + beta given du: accumulates dgamma / dbeta, returns dx (+ add).
+        relu_x: x is the output of a ReLU whose backward is applied to the result in the same pass."""
+        if rows_per_group > 1:  # GroupNorm frames: column sums and group sums share one pass over (du, x)
+            cs, ms = ops.norm_sums(du, x, mr, gamma, rows_per_group, count)
+        else:
+            cs = ops.col_sums(du, x, mr, rows_per_group)
+            ms = ops.group_sums(du, x, mr, gamma, rows_per_group, count)
         if g_param is not None:
             _acc(g_param[0], g_param[1](cs[0]))
             _acc(b_param[0], b_param[1](cs[1]))
-        ms = ops.group_sums(du, x, mr, gamma, rows_per_group, count)
-        return ops.norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=zp, add=add)
+        return ops.norm_bwd_apply(du, x, mr, gamma, ms, rows_per_group, zp=zp, add=add, relu_x=relu_x)
 
-    def _normconv_bwd(self, dz, x, mr, H, W, W_rot, names, P, add=None):
+    def _normconv_bwd(self, dz, x, mr, H, W, W_rot, names, P, add=None, relu_x=False):
         """dz: gradient wrt the conv output (ReLU already applied), ZP [F,H+1,W+1,Cout]; x: the layer input (ZP, pre-norm).
         Accumulates the weight / norm gradients and returns the gradient wrt x (+ add)."""
         Fn, Cin, Cout = x.shape[0], x.shape[3], dz.shape[3]
@@ -158,9 +162,9 @@ class BCTrainer:
         _acc(P[names + ".layer.weight"], dWk.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2))
         ident = lambda v: v
         return self._norm_bwd(du.view(R, Cin), x.view(R, Cin), mr, g32, (H + 1) * (W + 1), H * W * Cin, (gam, ident), (bet, ident),
-                              zp=(H, W, Cin), add=None if add is None else add.view(R, Cin)).view(x.shape)
+                              zp=(H, W, Cin), add=None if add is None else add.view(R, Cin), relu_x=relu_x).view(x.shape)
 
-    def _normlinear_bwd(self, dz, x, mr, Wt, names, P, add=None):
+    def _normlinear_bwd(self, dz, x, mr, Wt, names, P, add=None, relu_x=False):
         """[LayerNorm ->] Linear backward; dz [rows][out] is the gradient wrt the GEMM output (after ReLU masking)."""
         gam, bet = P[names + ".norm.weight"], P[names + ".norm.bias"]
         g32, b32 = gam.detach().float().contiguous(), bet.detach().float().contiguous()
@@ -169,7 +173,7 @@ class BCTrainer:
         self._wgrad_linear(dz, u, P[names + ".layer.weight"])
         del u
         ident = lambda v: v
-        return self._norm_bwd(du, x, mr, g32, 1, x.shape[1], (gam, ident), (bet, ident), add=add)
+        return self._norm_bwd(du, x, mr, g32, 1, x.shape[1], (gam, ident), (bet, ident), add=add, relu_x=relu_x)
 
     # -- the step ---------------------------------------------------------------------------------------------------------
     def loss_and_grad(self, img, first, state_in, actions):
@@ -217,19 +221,16 @@ class BCTrainer:
         # ---------------- final_ln (plain norm) + lastlayer ----------------
         ident = lambda v: v
         fg = P["final_ln.weight"]
-        dxl = self._norm_bwd(dlat, tape["xl"], tape["mr_xl"], fg.detach().float().contiguous(), 1, h, (fg, ident), (P["final_ln.bias"], ident))
-        dz = ops.relu_mask(dxl, tape["xl"])
-        dx = self._normlinear_bwd(dz, tape["z_last"], tape["mr_zl"], wts["last_t"], "lastlayer", P)
+        # (xl, z_last, x0, xd and the convs' h are ReLU outputs that feed a norm: their ReLU backward rides on that norm's apply pass)
+        dz = self._norm_bwd(dlat, tape["xl"], tape["mr_xl"], fg.detach().float().contiguous(), 1, h, (fg, ident), (P["final_ln.bias"], ident),
+                            relu_x=True)
+        dx = self._normlinear_bwd(dz, tape["z_last"], tape["mr_zl"], wts["last_t"], "lastlayer", P, relu_x=True)
         # ---------------- transformer blocks, last to first ----------------
         for l in reversed(range(cfg.n_layers)):
             self._dbg(f"recurrent_layer.blocks.{l}" if l < cfg.n_layers - 1 else "recurrent_out", dx)
             dx = self._block_bwd(l, dx, tape["blocks"][l], tape["first_u8"], wts["layers"][l], P, B, t, last=(l == cfg.n_layers - 1))
         # ---------------- img_process.linear, dense ----------------
-        self._dbg("img_process", dx)
-        dz = ops.relu_mask(dx, tape["x0"])
-        dxd = self._normlinear_bwd(dz, tape["xd"], tape["mr_d"], wts["linear_t"], "img_process.linear", P)
-        self._dbg("img_process.cnn.dense", dxd)
-        dz = ops.relu_mask(dxd, tape["xd"])
+        dz = self._normlinear_bwd(dx, tape["xd"], tape["mr_d"], wts["linear_t"], "img_process.linear", P, relu_x=True)
         dcnn = self._dense_bwd(dz, tape, wts, P)
         # ---------------- ImpalaCNN, last stack to first ----------------
         self._cnn_bwd(dcnn, tape, wts, P)
@@ -265,7 +266,7 @@ class BCTrainer:
         o = f"{b}.r.orc_block"
         N = B * t
         nr = 10 * heads
-        dz = ops.relu_mask(dzo, S["z"]) if last else dzo  # the F.relu of lib/policy.py:211 lives in the last block's epilogue
+        dz = dzo  # (last block: z is relu(..) (lib/policy.py:211 fused into its epilogue); lastlayer's norm backward already masked dzo)
         # mlp1: z = y + hmid W1^T + b1
         dh = self._gemm(dz, W["mlp1_t"], h * cfg.pointwise_ratio)
         self._wgrad_linear(dz, S["hmid"], P[f"{b}.mlp1.layer.weight"])
@@ -296,7 +297,8 @@ class BCTrainer:
         # pre_r_ln (plain norm of the block input)
         ident = lambda v: v
         g = P[f"{b}.pre_r_ln.weight"]
-        return self._norm_bwd(dxhat, S["x"], S["mr_x"], g.detach().float().contiguous(), 1, h, (g, ident), (P[f"{b}.pre_r_ln.bias"], ident))
+        return self._norm_bwd(dxhat, S["x"], S["mr_x"], g.detach().float().contiguous(), 1, h, (g, ident), (P[f"{b}.pre_r_ln.bias"], ident),
+                              relu_x=(l == 0))  # block 0's input is relu(img_process.linear)
 
     def _cnn_bwd(self, dout, tape, wts, P):
         """Backward of lib/impala_cnn.py:187-195; `dout` is the gradient wrt the last stack's output (ZP)."""
@@ -317,10 +319,9 @@ class BCTrainer:
                 mr_in = rec["blocks"][j - 1]["mr"] if j == 1 else rec["mr0"]
                 # x_out = x_in + relu(conv1(GN(h)));  h = relu(conv0(GN(x_in)))
                 dz1 = ops.relu_mask(dx, blk["r"])
-                dh = self._normconv_bwd(dz1, blk["h"], blk["mrh"], H, W, wts["stacks"][i]["convs"][2 * j + 1], f"{s}.blocks.{j}.conv1", P)
+                dz0 = self._normconv_bwd(dz1, blk["h"], blk["mrh"], H, W, wts["stacks"][i]["convs"][2 * j + 1], f"{s}.blocks.{j}.conv1", P,
+                                         relu_x=True)
                 del dz1
-                dz0 = ops.relu_mask(dh, blk["h"])
-                del dh
                 dx = self._normconv_bwd(dz0, x_in, mr_in, H, W, wts["stacks"][i]["convs"][2 * j], f"{s}.blocks.{j}.conv0", P, add=dx)
                 del dz0
             self._dbg(f"{s}.n", dx)
@@ -336,7 +337,7 @@ class BCTrainer:
                 _acc(P[f"{s}.firstconv.layer.weight"], (dWk / 255.0).view(C, 3, 3, 3).permute(0, 3, 1, 2))
                 _acc(P[f"{s}.firstconv.layer.bias"], db)
             else:
-                dfull = ops.maxpool3s2_bwd(dy1, rec["full"], rec["y1"])  # includes the ReLU in front of the pool
+                dfull = ops.maxpool3s2_bwd(dy1, rec["full"])  # includes the ReLU in front of the pool
                 del dy1
                 dx = self._normconv_bwd(dfull, rec["x_in"], rec["mr_in"], rec["H_in"], rec["W_in"], wts["stacks"][i]["first"],
                                         f"{s}.firstconv", P)
