@@ -210,7 +210,15 @@ int vpt_gather_logprob(const float* logits, const int64_t* idx, float* lp, int64
  *   src u8 [F][Hs][Ws][C] -> dst u8 [F][Hd][Wd][C]
  * -------------------------------------------------------------------------------------------------------- */
 int vpt_resize_bilinear_u8(const uint8_t* src, uint8_t* dst, const int32_t* xidx, const int16_t* xw, const int32_t* yidx,
-                           const int16_t* yw, int32_t F, int32_t Hs, int32_t Ws, int32_t Hd, int32_t Wd, int32_t C, void* stream);
+                           const int16_t* yw, int32_t F, int32_t Hs, int32_t Ws, int32_t Hd, int32_t Wd, int32_t C, int32_t swap_rb,
+                           void* stream);
+/* swap_rb != 0 additionally exchanges channels 0 and 2 (cv2.cvtColor(frame, COLOR_BGR2RGB), data_loader.py:116).
+ *
+ * Cursor overlay of the BC data loader (data_loader.py:34-45,108-115), in place on frames u8 [F][H][W][3]: for every frame with
+ * xy[f] = (x, y) >= 0:  frame[y:y+ch, x:x+cw] = uint8(frame * (1 - alpha) + cursor * alpha)  in float64 with numpy's truncation,
+ * clipped at the right / bottom border; xy[f].x < 0 = no cursor.  cursor u8 [ch][cw][3], alpha f64 [ch][cw]. */
+int vpt_composite_cursor_u8(uint8_t* frames, const uint8_t* cursor, const double* alpha, const int32_t* xy, int32_t F, int32_t H, int32_t W,
+                            int32_t ch, int32_t cw, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
  * BC step groundwork (behavioural_cloning.py:63-67,119-123): fused torch.optim.Adam(lr, weight_decay) step over ONE flat fp32

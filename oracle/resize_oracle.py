@@ -38,3 +38,23 @@ def resize_linear_u8(img, dw, dh):
     y1 = np.minimum(yi + 1, H - 1)
     out = ((ya[:, 0, None, None] * (hor[yi] >> 4)) >> 16) + ((ya[:, 1, None, None] * (hor[y1] >> 4)) >> 16)
     return np.clip((out + 2) >> 2, 0, 255).astype(np.uint8)
+
+
+def composite_cursor(frame, cursor, alpha, x, y):
+    """data_loader.py:34-45 (composite_images_with_alpha): frame uint8 [H, W, 3] modified in place; cursor uint8 [ch, cw, 3];
+    alpha float64 [ch, cw, 1]; float64 arithmetic, astype(uint8) truncation, overlay clipped at the right / bottom border."""
+    ch = max(0, min(frame.shape[0] - y, cursor.shape[0]))
+    cw = max(0, min(frame.shape[1] - x, cursor.shape[1]))
+    if ch == 0 or cw == 0:
+        return frame
+    a = alpha[:ch, :cw]
+    frame[y:y + ch, x:x + cw, :] = (frame[y:y + ch, x:x + cw, :] * (1 - a) + cursor[:ch, :cw, :] * a).astype(np.uint8)
+    return frame
+
+
+def ingest(frame_bgr, size, cursor=None, alpha=None, xy=None):
+    """data_loader.py:108-118: [cursor overlay] -> BGR2RGB -> resize (INTER_LINEAR) -> uint8 [size[1], size[0], 3]."""
+    f = frame_bgr.copy()
+    if cursor is not None and xy is not None and xy[0] >= 0:
+        composite_cursor(f, cursor, alpha, int(xy[0]), int(xy[1]))
+    return resize_linear_u8(f[:, :, ::-1], size[0], size[1])

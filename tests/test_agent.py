@@ -104,3 +104,80 @@ def test_minerl_agent_rollout_smoke():
     agent.reset()
     back = agent._env_action_to_agent({k: (np.asarray(v) if k == "camera" else np.asarray(v)) for k, v in act.items()})
     assert back["buttons"].shape == (1, 1) and back["camera"].shape == (1, 1)
+
+
+def test_checkpoint_io_roundtrip(tmp_path):
+    """f-4: `.model` pickle -> constructor kwargs (run_agent.py:11-14), `.weights` round trip on the reference schema
+    (agent.py:132-135, behavioural_cloning.py:131-132), optimizer state save / resume."""
+    import pickle
+
+    import vpt_b200
+    from common import make_policy, small_kwargs
+    from video_pre_training_b200.parallel import FlatAdamDP
+
+    kw = small_kwargs()
+    model_file = tmp_path / "tiny.model"
+    with open(model_file, "wb") as fh:  # the layout of the released .model files
+        pickle.dump({"model": {"args": {"net": {"args": kw}, "pi_head_opts": {"temperature": "2.0"}}}}, fh)
+    pk, hk = vpt_b200.load_model_parameters(str(model_file))
+    assert pk == kw and hk == {"temperature": 2.0} and isinstance(hk["temperature"], float)
+
+    pol, sd, _ = make_policy(kw, seed=3)
+    opt = FlatAdamDP([p for n, p in pol.named_parameters() if not n.startswith("value_head")], lr=1e-3, weight_decay=0.01)
+    assert pol.net.final_ln.weight.data_ptr() >= opt.flat_p.data_ptr()  # parameters now live in the flat bucket
+    vpt_b200.save_weights(pol, str(tmp_path / "a.weights"))
+    loaded = torch.load(tmp_path / "a.weights")
+    assert list(loaded.keys()) == list(sd.keys()) and all(torch.equal(loaded[k], sd[k]) for k in sd)
+    assert all(v.is_contiguous() and v.untyped_storage().nbytes() == v.numel() * v.element_size() for v in loaded.values())
+
+    pol2, _, _ = make_policy(kw, seed=4)
+    opt2 = FlatAdamDP([p for n, p in pol2.named_parameters() if not n.startswith("value_head")], lr=5e-4)
+    opt.exp_avg.normal_(); opt.exp_avg_sq.uniform_(); opt.t = 17
+    vpt_b200.save_training_state(str(tmp_path / "run.pt"), pol, opt)
+    vpt_b200.load_training_state(str(tmp_path / "run.pt"), pol2, opt2)
+    assert all(torch.equal(a, b) for a, b in zip(pol.state_dict().values(), pol2.state_dict().values()))
+    assert torch.equal(opt.exp_avg, opt2.exp_avg) and torch.equal(opt.exp_avg_sq, opt2.exp_avg_sq)
+    assert opt2.t == 17 and opt2.lr == 1e-3 and opt2.weight_decay == 0.01
+    assert pol2.net.final_ln.weight.data_ptr() >= opt2.flat_p.data_ptr()  # still aliased after the in-place load
+
+
+def _cursor(rng):
+    png = rng.integers(0, 256, (16, 16, 4), dtype=np.uint8)  # stand-in for cursors/mouse_cursor_white_16x16.png (BGRA)
+    png[:4, :4, 3] = 0
+    png[4:8, 4:8, 3] = 255
+    return np.ascontiguousarray(png[:, :, :3]), png[:, :, 3:] / 255.0  # data_loader.py:78-83
+
+
+def test_ingest_oracle_matches_reference_arithmetic():
+    """The oracle's cursor overlay is the reference's numpy expression (data_loader.py:34-45), incl. clipping at the border, and
+    its ingest = overlay -> cv2.cvtColor(BGR2RGB) -> cv2.resize, checked against cv2 where it is importable."""
+    rng = np.random.default_rng(5)
+    cur, alpha = _cursor(rng)
+    frame = rng.integers(0, 256, (360, 640, 3), dtype=np.uint8)
+    for (x, y) in [(0, 0), (100, 37), (630, 350), (639, 359), (700, 10)]:
+        got = resize_oracle.composite_cursor(frame.copy(), cur, alpha, x, y)
+        exp = frame.copy()
+        ch, cw = max(0, min(360 - y, 16)), max(0, min(640 - x, 16))
+        if ch and cw:
+            a = alpha[:ch, :cw]
+            exp[y:y + ch, x:x + cw, :] = (exp[y:y + ch, x:x + cw, :] * (1 - a) + cur[:ch, :cw, :] * a).astype(np.uint8)
+        assert np.array_equal(got, exp)
+        if cv2 is not None:
+            ref = exp.copy()
+            cv2.cvtColor(ref, code=cv2.COLOR_BGR2RGB, dst=ref)
+            ref = cv2.resize(ref, (128, 128), interpolation=cv2.INTER_LINEAR)
+            assert np.array_equal(resize_oracle.ingest(frame, (128, 128), cur, alpha, (x, y)), ref)
+
+
+@pytest.mark.gpu
+def test_ingest_kernels_bit_exact():
+    rng = np.random.default_rng(6)
+    cur, alpha = _cursor(rng)
+    F_, H, W = 6, 360, 640
+    frames = rng.integers(0, 256, (F_, H, W, 3), dtype=np.uint8)
+    xy = np.array([[0, 0], [100, 37], [-1, -1], [630, 350], [639, 359], [700, 10]], dtype=np.int32)
+    got = A.ingest_frames(torch.from_numpy(frames).cuda(), torch.from_numpy(cur).cuda(), torch.from_numpy(alpha[:, :, 0].copy()).cuda(),
+                          torch.from_numpy(xy).cuda()).cpu().numpy()
+    for f in range(F_):
+        exp = resize_oracle.ingest(frames[f], (128, 128), cur, alpha, xy[f])
+        assert np.array_equal(got[f], exp), f

@@ -111,3 +111,56 @@ def test_shard_range_covers_everything():
             spans = [parallel.shard_range(B, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == B
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _bc_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vpt_b200  # noqa: F401
+    from common import emulation, make_policy, small_kwargs
+    from video_pre_training_b200 import parallel
+    from video_pre_training_b200.training import BCTrainer
+
+    pol, _, _ = make_policy(small_kwargs(), seed=0)  # identical replicas
+    B, T = 4, 8
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (B, T, 32, 32, 3), dtype=torch.uint8, generator=g)
+    first = torch.zeros(B, T, dtype=torch.bool)
+    actions = {"camera": torch.randint(0, 121, (B, T, 1), generator=g), "buttons": torch.randint(0, 8641, (B, T, 1), generator=g)}
+    named = [(n, p) for n, p in pol.named_parameters() if not n.startswith("value_head")]
+    opt = parallel.FlatAdamDP([p for _, p in named], lr=1e-3)
+    lo, hi = parallel.shard_range(B, rank, world)
+    with emulation():
+        opt.zero_grad()
+        BCTrainer(pol).loss_and_grad(img[lo:hi], first[lo:hi], pol.initial_state(hi - lo), {k: v[lo:hi] for k, v in actions.items()})
+        w = opt.reduce_gradients()                      # the step's single collective
+        dp_grad = opt.flat_g.clone() / w                # (the 1/world lives in the Adam kernel)
+        if rank == 0:                                   # the same global batch in one process
+            opt.zero_grad()
+            BCTrainer(pol).loss_and_grad(img, first, pol.initial_state(B), actions)
+            err = ((dp_grad - opt.flat_g).norm() / opt.flat_g.norm()).item()
+            q.put((rank, w, err))
+        else:
+            q.put((rank, w, 0.0))
+    dist.destroy_process_group()
+
+
+def test_bc_data_parallel_gradients_equal_the_global_batch_gloo():
+    """BC step over 2 ranks: clips sharded across ranks, replicated weights, ONE all-reduce of the flat gradient
+    bucket; the averaged result equals the gradient of the whole batch computed in one process (sequences are independent, the
+    loss is a mean over frames; bf16 rounding of per-rank partial sums is the only difference)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_bc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(w == 2 for _, w, _ in res)
+    assert res[0][2] < 2e-2, res

@@ -149,8 +149,9 @@ def _linear_tables(dst: int, src: int):
 _TABLE_CACHE = {}
 
 
-def resize_frames(frames: torch.Tensor, size=AGENT_RESOLUTION) -> torch.Tensor:
-    """uint8 CUDA frames [F, Hs, Ws, C] -> [F, size[1], size[0], C], bit-exact with cv2.resize(frame, size, INTER_LINEAR)."""
+def resize_frames(frames: torch.Tensor, size=AGENT_RESOLUTION, bgr_to_rgb: bool = False) -> torch.Tensor:
+    """uint8 CUDA frames [F, Hs, Ws, C] -> [F, size[1], size[0], C], bit-exact with cv2.resize(frame, size, INTER_LINEAR);
+    bgr_to_rgb also applies cv2.cvtColor(frame, COLOR_BGR2RGB) (data_loader.py:116) in the same pass."""
     if not frames.is_cuda or frames.dtype != torch.uint8:
         raise nat.NativeError("resize_frames needs a uint8 CUDA tensor (no CPU fallback)")
     frames = frames.contiguous()
@@ -168,8 +169,30 @@ def resize_frames(frames: torch.Tensor, size=AGENT_RESOLUTION) -> torch.Tensor:
     xi, xw, yi, yw = _TABLE_CACHE[key]
     out = torch.empty((F_, Hd, Wd, C), dtype=torch.uint8, device=frames.device)
     nat.check(nat.lib().vpt_resize_bilinear_u8(frames.data_ptr(), out.data_ptr(), xi.data_ptr(), xw.data_ptr(), yi.data_ptr(), yw.data_ptr(),
-                                               F_, Hs, Ws, Hd, Wd, C, torch.cuda.current_stream().cuda_stream), "vpt_resize_bilinear_u8")
+                                               F_, Hs, Ws, Hd, Wd, C, int(bgr_to_rgb), torch.cuda.current_stream().cuda_stream), "vpt_resize_bilinear_u8")
     return out
+
+
+def composite_cursor(frames: torch.Tensor, cursor: torch.Tensor, alpha: torch.Tensor, xy: torch.Tensor) -> torch.Tensor:
+    """In-place cursor overlay of data_loader.py:34-45 on uint8 CUDA frames [F, H, W, 3]: cursor uint8 [ch, cw, 3], alpha float64
+    [ch, cw] (= cursor_png[..., 3] / 255.0), xy int32 [F, 2] top-left corner per frame ((-1, -1) = GUI closed, frame untouched)."""
+    if not frames.is_cuda or frames.dtype != torch.uint8 or not frames.is_contiguous():
+        raise nat.NativeError("composite_cursor needs a contiguous uint8 CUDA tensor (no CPU fallback)")
+    F_, H, W, C = frames.shape
+    assert C == 3 and cursor.dtype == torch.uint8 and alpha.dtype == torch.float64 and xy.dtype == torch.int32 and tuple(xy.shape) == (F_, 2)
+    ch, cw = cursor.shape[:2]
+    nat.check(nat.lib().vpt_composite_cursor_u8(frames.data_ptr(), cursor.contiguous().data_ptr(), alpha.contiguous().data_ptr(),
+                                                xy.contiguous().data_ptr(), F_, H, W, ch, cw, torch.cuda.current_stream().cuda_stream),
+              "vpt_composite_cursor_u8")
+    return frames
+
+
+def ingest_frames(frames_bgr: torch.Tensor, cursor=None, alpha=None, cursor_xy=None, size=AGENT_RESOLUTION) -> torch.Tensor:
+    """The BC data loader's per-frame image path on the GPU (data_loader.py:108-118): cursor overlay where the GUI is open ->
+    BGR to RGB -> bilinear resize to the agent resolution; uint8 in, uint8 out, bit-exact with the numpy / cv2 code."""
+    if cursor is not None:
+        frames_bgr = composite_cursor(frames_bgr, cursor, alpha, cursor_xy)
+    return resize_frames(frames_bgr, size, bgr_to_rgb=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -198,7 +221,8 @@ class MineRLAgent:
 
     def load_weights(self, path):
         """agent.py:132-135."""
-        self.policy.load_state_dict(torch.load(path, map_location=self.device), strict=False)
+        from .checkpoint import load_weights
+        load_weights(self.policy, path, map_location=self.device)
         self.reset()
 
     def reset(self):

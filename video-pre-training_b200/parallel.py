@@ -100,6 +100,19 @@ class FlatAdamDP:
     def zero_grad(self):
         self.flat_g.zero_()
 
+    def state_dict(self):
+        """Moments, step count and hyper-parameters (CPU tensors); the bucket layout is implied by the parameter order."""
+        return {"step": self.t, "n": self.n, "exp_avg": self.exp_avg.detach().cpu().clone(), "exp_avg_sq": self.exp_avg_sq.detach().cpu().clone(),
+                "lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        if sd["n"] != self.n:
+            raise ValueError(f"FlatAdamDP: bucket size {sd['n']} in the checkpoint != {self.n} (different parameter set)")
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.t = int(sd["step"])
+        self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
+
     def reduce_gradients(self) -> int:
         """The single gradient all-reduce (sum) of the BC step; returns the world size (the mean is folded into the Adam kernel)."""
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
