@@ -125,7 +125,15 @@ if a.ops and rank == 0:
     for n, e0, e1 in rec:
         tot[n] += e0.elapsed_time(e1)
         cnt[n] += 1
-    print(f"instrumented step: fwd+bwd {s0.elapsed_time(s1):.1f} ms, adam {s1.elapsed_time(s2):.1f} ms; sum of ops {sum(tot.values()):.1f} ms")
+    p0, p1, p2 = ev(), ev(), ev()   # weight re-layout (every parameter changed in opt.step): forward folds, backward transposes
+    p0.record()
+    pol.net.prepared(); pol._heads_prepared()
+    p1.record()
+    tr._weights()
+    p2.record()
+    torch.cuda.synchronize()
+    print(f"instrumented step: fwd+bwd {s0.elapsed_time(s1):.1f} ms, adam {s1.elapsed_time(s2):.1f} ms; sum of ops {sum(tot.values()):.1f} ms; "
+          f"weight re-layout after the step: forward {p0.elapsed_time(p1):.1f} ms + backward {p1.elapsed_time(p2):.1f} ms")
     for n, t in sorted(tot.items(), key=lambda kv: -kv[1]):
         print(f"  {t:8.2f} ms  n={cnt[n]:4d}  {n}")
 if world > 1:

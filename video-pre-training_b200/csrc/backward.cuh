@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
     if (active) {
+#pragma unroll 4
         for (long long r = r_begin + rl; r < r_end; r += 8) {
             float d[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(du + r * ld_du + cv * 8)), d);
@@ -420,7 +421,7 @@ static inline int col_sums_slabs(long long rows, int C) {
 // slabs per statistics group of the fused (column + group sums) pass
 static inline int norm_sums_spg(long long groups, int rows_per_group, int C) {
     const int colblocks = (C / 8 + 31) / 32;
-    long long spg = (4LL * 148 + colblocks * groups - 1) / (colblocks * groups);
+    long long spg = (32LL * 148 + colblocks * groups - 1) / (colblocks * groups);  // several waves of 8 resident blocks per SM
     const long long max_spg = (rows_per_group + 63) / 64;
     if (spg > max_spg) spg = max_spg;
     if (spg < 1) spg = 1;

@@ -179,32 +179,49 @@ def _net_schema(cfg: NetConfig) -> "OrderedDict[str, torch.Tensor]":
 # ---------------------------------------------------------------------------------------------------------------
 # kernel-side weight layouts
 # ---------------------------------------------------------------------------------------------------------------
+_CLASS_TAPS = None
+
+
+def _class_taps(device):
+    """[9 border classes][9 taps] 0/1 matrix (float64): which taps of a 3x3 pad-1 convolution read inside the image for an output
+    pixel of border class (cy, cx), cy / cx in {first row / column, interior, last row / column}."""
+    global _CLASS_TAPS
+    if _CLASS_TAPS is None or _CLASS_TAPS.device != device:
+        valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}
+        m = torch.zeros(9, 9, dtype=torch.float64)
+        for cy in range(3):
+            for cx in range(3):
+                for ky in valid[cy]:
+                    for kx in valid[cx]:
+                        m[cy * 3 + cx, ky * 3 + kx] = 1.0
+        _CLASS_TAPS = m.to(device)
+    return _CLASS_TAPS
+
+
 def _fold_conv(W, gamma, beta):
     """GroupNorm(1) -> conv3x3(pad 1) fold:
     conv(GN(x))[o,p] = rstd*conv_{W*gamma}(x)[o,p] - rstd*mean*S1[cls(p)][o] + S2[cls(p)][o].
-    S1 is summed from the bf16-ROUNDED weights (the ones the tensor cores multiply) so the mean term cancels exactly."""
+    S1 is summed from the bf16-ROUNDED weights (the ones the tensor cores multiply) so the mean term cancels exactly.
+    (Runs after every optimizer step of a BC run, hence a handful of batched ops rather than a loop over the 9 classes.)"""
+    Cout = W.shape[0]
     Wg = (W * gamma[None, :, None, None]).permute(0, 2, 3, 1).contiguous()  # [Cout, ky, kx, Cin]
     Wb = Wg.to(BF16)
-    tg = Wb.double().sum(-1)                                                # [Cout, 3, 3]
-    tb = (W.double() * beta.double()[None, :, None, None]).sum(1)           # [Cout, 3, 3]
-    valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}                            # row/col class -> in-bounds taps
-    S1 = torch.empty(9, W.shape[0], dtype=torch.float64, device=W.device)
-    S2 = torch.empty_like(S1)
-    for cy in range(3):
-        for cx in range(3):
-            S1[cy * 3 + cx] = tg[:, valid[cy]][:, :, valid[cx]].sum((1, 2))
-            S2[cy * 3 + cx] = tb[:, valid[cy]][:, :, valid[cx]].sum((1, 2))
-    return Wb.reshape(W.shape[0], -1).contiguous(), S1.float().contiguous(), S2.float().contiguous()
+    tg = Wb.sum(-1, dtype=torch.float64).reshape(Cout, 9)                                  # per-tap sums of W*gamma
+    tb = (W * beta[None, :, None, None]).sum(1, dtype=torch.float64).reshape(Cout, 9)      # per-tap sums of W*beta
+    M = _class_taps(W.device)
+    S1 = (M @ tg.t()).float().contiguous()  # [9, Cout]
+    S2 = (M @ tb.t()).float().contiguous()
+    return Wb.reshape(Cout, -1).contiguous(), S1, S2
 
 
 def _fold_linear(W, gamma=None, beta=None, bias=None):
     """[LayerNorm ->] Linear fold: out = rstd*(x @ (W*gamma)^T) - rstd*mean*S1 + S2, S2 = W @ beta (+ bias)."""
     Wg = W if gamma is None else W * gamma[None, :]
     Wb = Wg.to(BF16).contiguous()
-    S1 = Wb.double().sum(1).float().contiguous() if gamma is not None else None
+    S1 = Wb.sum(1, dtype=torch.float64).float().contiguous() if gamma is not None else None
     S2 = None
     if beta is not None:
-        S2 = (W.double() @ beta.double())
+        S2 = (W * beta[None, :]).sum(1, dtype=torch.float64)
     if bias is not None:
         S2 = bias.double() if S2 is None else S2 + bias.double()
     return Wb, S1, (S2.float().contiguous() if S2 is not None else None)
