@@ -110,7 +110,7 @@ __global__ void sums_finalize_kernel(const float2* __restrict__ part, float2* __
 // norm backward 2/3: per channel  (sum_rows du*n, sum_rows du);  block = 32 channel vectors x 8 row lanes,
 // grid = (ceil(C8/32), S row slabs); partials [S][2][C] summed in a fixed order by col_sums_finalize_kernel
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __restrict__ du, long long ld_du, const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) col_sums_kernel(const __nv_bfloat16* __restrict__ du, long long ld_du, const __nv_bfloat16* __restrict__ x,
                                                          const float2* __restrict__ mr, const float* __restrict__ gamma, float* __restrict__ ws,
                                                          float2* __restrict__ gpart, long long rows, int C, int rows_per_group, int slabs_per_group,
                                                          long long rows_per_slab) {
@@ -136,19 +136,35 @@ __global__ void __launch_bounds__(256) col_sums_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
     if (active) {
-#pragma unroll 4
-        for (long long r = r_begin + rl; r < r_end; r += 8) {
-            float d[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(du + r * ld_du + cv * 8)), d);
-            if (x != nullptr) {
-                float xv[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * (long long)C + cv * 8)), xv);
-                if (slabs_per_group == 0) st = __ldg(mr + (rows_per_group == 1 ? r : r / rows_per_group));
+        // 4 rows per trip with all 8 loads issued before the first use (ncu: the one-row loop ran at half of HBM bandwidth, latency bound)
+        for (long long r = r_begin + rl; r < r_end; r += 32) {
+            uint4 dv[4], xr[4];
+            float2 sv[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a0[j] = fmaf(d[j], (xv[j] - st.x) * st.y, a0[j]);
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = r + 8 * u;
+                dv[u] = xr[u] = make_uint4(0, 0, 0, 0);  // bf16 zeros: a row past the slab adds nothing
+                sv[u] = st;
+                if (rr < r_end) {
+                    dv[u] = __ldg(reinterpret_cast<const uint4*>(du + rr * ld_du + cv * 8));
+                    if (x != nullptr) {
+                        xr[u] = __ldg(reinterpret_cast<const uint4*>(x + rr * (long long)C + cv * 8));
+                        if (slabs_per_group == 0) sv[u] = __ldg(mr + (rows_per_group == 1 ? rr : rr / rows_per_group));
+                    }
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a1[j] += d[j];
+            for (int u = 0; u < 4; ++u) {
+                float d[8], xv[8];
+                unpack8(dv[u], d);
+                unpack8(xr[u], xv);
+                if (x != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a0[j] = fmaf(d[j], (xv[j] - sv[u].x) * sv[u].y, a0[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a1[j] += d[j];
+            }
         }
     }
 #pragma unroll
