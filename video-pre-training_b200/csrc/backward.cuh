@@ -110,6 +110,8 @@ __global__ void sums_finalize_kernel(const float2* __restrict__ part, float2* __
 // norm backward 2/3: per channel  (sum_rows du*n, sum_rows du);  block = 32 channel vectors x 8 row lanes,
 // grid = (ceil(C8/32), S row slabs); partials [S][2][C] summed in a fixed order by col_sums_finalize_kernel
 // ---------------------------------------------------------------------------------------------------------
+// kRowStats: every row may belong to another statistics group (LayerNorm rows, or slabs that straddle groups)
+template <bool kRowStats>
 __global__ void __launch_bounds__(256, 3) col_sums_kernel(const __nv_bfloat16* __restrict__ du, long long ld_du, const __nv_bfloat16* __restrict__ x,
                                                          const float2* __restrict__ mr, const float* __restrict__ gamma, float* __restrict__ ws,
                                                          float2* __restrict__ gpart, long long rows, int C, int rows_per_group, int slabs_per_group,
@@ -139,17 +141,17 @@ __global__ void __launch_bounds__(256, 3) col_sums_kernel(const __nv_bfloat16* _
         // 4 rows per trip with all 8 loads issued before the first use (ncu: the one-row loop ran at half of HBM bandwidth, latency bound)
         for (long long r = r_begin + rl; r < r_end; r += 32) {
             uint4 dv[4], xr[4];
-            float2 sv[4];
+            float2 sv[kRowStats ? 4 : 1];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const long long rr = r + 8 * u;
                 dv[u] = xr[u] = make_uint4(0, 0, 0, 0);  // bf16 zeros: a row past the slab adds nothing
-                sv[u] = st;
+                if (kRowStats) sv[u] = st;
                 if (rr < r_end) {
                     dv[u] = __ldg(reinterpret_cast<const uint4*>(du + rr * ld_du + cv * 8));
                     if (x != nullptr) {
                         xr[u] = __ldg(reinterpret_cast<const uint4*>(x + rr * (long long)C + cv * 8));
-                        if (slabs_per_group == 0) sv[u] = __ldg(mr + (rows_per_group == 1 ? rr : rr / rows_per_group));
+                        if (kRowStats) sv[u] = __ldg(mr + (rows_per_group == 1 ? rr : rr / rows_per_group));
                     }
                 }
             }
@@ -159,8 +161,9 @@ __global__ void __launch_bounds__(256, 3) col_sums_kernel(const __nv_bfloat16* _
                 unpack8(dv[u], d);
                 unpack8(xr[u], xv);
                 if (x != nullptr) {
+                    const float2 su = kRowStats ? sv[u] : st;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a0[j] = fmaf(d[j], (xv[j] - sv[u].x) * sv[u].y, a0[j]);
+                    for (int j = 0; j < 8; ++j) a0[j] = fmaf(d[j], (xv[j] - su.x) * su.y, a0[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a1[j] += d[j];
@@ -455,7 +458,7 @@ extern "C" int vpt_col_sums(const void* du, int64_t ld_du, const void* x, const 
     const int S = col_sums_slabs(rows, C);
     const long long per = (rows + S - 1) / S;
     dim3 grid((C / 8 + 31) / 32, S);
-    col_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(du), ld_du, reinterpret_cast<const __nv_bfloat16*>(x),
+    col_sums_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(du), ld_du, reinterpret_cast<const __nv_bfloat16*>(x),
                                                            reinterpret_cast<const float2*>(mr), nullptr, workspace, nullptr, rows, C,
                                                            rows_per_group > 0 ? rows_per_group : 1, 0, per);
     VPT_LAUNCH_CHECK();
@@ -486,7 +489,7 @@ extern "C" int vpt_norm_sums(const void* du, const void* x, const float* mr, con
     float* ws_cols = workspace;
     float2* gpart = reinterpret_cast<float2*>(workspace + S * 2 * C);
     dim3 grid(colblocks, (unsigned)S);
-    col_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(du), C, reinterpret_cast<const __nv_bfloat16*>(x),
+    col_sums_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(du), C, reinterpret_cast<const __nv_bfloat16*>(x),
                                                            reinterpret_cast<const float2*>(mr), gamma, ws_cols, gpart, rows, C, rows_per_group, spg, per);
     VPT_LAUNCH_CHECK();
     col_sums_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(ws_cols, out, 2 * C, (int)S);
