@@ -100,3 +100,27 @@ def test_bc_step_with_bf16_rounding_points_emulated(emulated):
             assert torch.isfinite(g).all()
             cos = (g * g_o).sum() / (g.norm() * g_o.norm()).clamp(min=1e-20)
             assert cos > 0.8, (n, cos.item())
+
+
+def test_trainer_refuses_what_the_reference_does_not_train():
+    pol, _, _ = make_policy(small_kwargs())
+    with pytest.raises(TypeError):
+        BCTrainer(pol.net)  # needs the agent policy (heads + loss), behavioural_cloning.py:54-62
+    idm = vpt_b200.InverseActionPolicy(vpt_b200.idm_action_space(), dict(temperature=2.0),
+                                       vpt_b200.idm_net_kwargs(img_shape=[32, 32, 128], hidsize=256, attention_heads=2, timesteps=8,
+                                                               attention_memory_size=8, n_recurrence_layers=1, impala_width=4))
+    with pytest.raises(TypeError):
+        BCTrainer(idm)
+
+
+def test_kv_memory_is_detached_between_steps(emulated):
+    """behavioural_cloning.py:111: the state carried to the next chunk must not require grad or alias the tape."""
+    pol, _, _ = make_policy(small_kwargs())
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (1, 8, 32, 32, 3), dtype=torch.uint8, generator=g)
+    first = torch.zeros(1, 8, dtype=torch.bool)
+    actions = {"camera": torch.randint(0, 121, (1, 8, 1), generator=g), "buttons": torch.randint(0, 8641, (1, 8, 1), generator=g)}
+    _, st = BCTrainer(pol).loss_and_grad(img, first, pol.initial_state(1), actions)
+    for mask, (k, v) in st:
+        assert mask.dtype == torch.bool and not k.requires_grad and not v.requires_grad and k.dtype == torch.float32
+        assert k.shape == (1, 8, 256)

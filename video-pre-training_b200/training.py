@@ -17,8 +17,6 @@ What each layer type needs (u = gamma * n + beta is the normalised layer input, 
 The KV memory carried in `state_in` is detached exactly like behavioural_cloning.py:111 (`tree_map(lambda x: x.detach())`),
 and `value_head.*` receives no gradient (None in the reference: the BC loss never touches it).
 """
-from collections import OrderedDict
-
 import torch
 
 from . import ops
@@ -81,7 +79,6 @@ class BCTrainer:
             if i > 0:
                 st["first"] = _rot(P[f"{s}.firstconv.layer.weight"])
             w["stacks"].append(st)
-        prep = net.prepared()
         Hf, Wf = cfg.final_hw
         C2 = cfg.chans[-1]
 
@@ -90,7 +87,6 @@ class BCTrainer:
             v = torch.nn.functional.pad(v, (0, 0, 0, 1, 0, 1))
             return v.reshape(*v.shape[:-3], -1)
 
-        w["perm"] = perm
         w["dense_t"] = _tr(perm(P[f"{pfx}.dense.layer.weight"].detach()))
         w["dense_g"] = perm(P[f"{pfx}.dense.norm.weight"].detach()).float().contiguous()
         w["dense_b"] = perm(P[f"{pfx}.dense.norm.bias"].detach()).float().contiguous()
@@ -110,7 +106,6 @@ class BCTrainer:
         self.ld_logits = (self.ntot + 7) // 8 * 8
         cat = torch.cat([getattr(pol.pi_head, name).linear_layer.weight for name in pol.head_specs], 0)
         w["heads_t"] = _tr(cat, self.ld_logits)
-        del prep
         self._wprep, self._wprep_fp = w, fp
         return w
 
@@ -124,11 +119,9 @@ class BCTrainer:
         return out
 
     @staticmethod
-    def _wgrad_linear(dz, u, weight_param=None, rows_out=None):
+    def _wgrad_linear(dz, u, weight_param=None):
         """dW [out][in] = dz^T u (tcgen05 GEMM over the token dimension); accumulated into `weight_param.grad` when given."""
         dW = ops.wgrad(dz, u)
-        if rows_out is not None:
-            dW = dW[:rows_out]
         if weight_param is not None:
             _acc(weight_param, dW)
         return dW
