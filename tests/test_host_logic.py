@@ -79,3 +79,21 @@ def test_unsupported_configs_are_refused(emulated):
     pol, _, _ = make_policy(small_kwargs(), pert=False)
     with pytest.raises(AssertionError):
         pol.net._forward_impl(torch.zeros(1, 1, 32, 32, 3, dtype=torch.uint8), torch.zeros(1, 1, dtype=torch.bool), [])
+
+
+def test_flat_bucket_clip_matches_torch():
+    from video_pre_training_b200.parallel import FlatAdamDP
+
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(7, 5)), torch.nn.Parameter(torch.randn(11))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    opt = FlatAdamDP(params, lr=1e-3)
+    for p, r in zip(params, ref):
+        g = torch.randn_like(p) * 3
+        p.grad.copy_(g)  # gradients live in the flat bucket
+        r.grad = g.clone()
+    total_ref = torch.nn.utils.clip_grad_norm_(ref, 5.0)
+    total = opt.clip_grad_norm_(5.0)
+    assert torch.allclose(total, total_ref) and total > 5.0
+    for p, r in zip(params, ref):
+        assert torch.allclose(p.grad, r.grad, rtol=1e-6, atol=1e-7)

@@ -120,8 +120,19 @@ class FlatAdamDP:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
         return world
 
-    def step(self):
+    def clip_grad_norm_(self, max_norm: float, world: int = 1):
+        """`th.nn.utils.clip_grad_norm_` over the whole (already reduced) bucket, without a host sync.  NOTE: the reference's own call
+        (behavioural_cloning.py:119) is a no-op -- it passes the `policy.parameters()` generator that the Adam constructor has
+        already exhausted -- so `step()` does not clip unless asked to."""
+        total = torch.linalg.vector_norm(self.flat_g) / world
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        self.flat_g.mul_(coef)
+        return total
+
+    def step(self, max_grad_norm=None):
         world = self.reduce_gradients()
+        if max_grad_norm is not None:
+            self.clip_grad_norm_(max_grad_norm, world)
         self.t += 1
         if self.flat_p.is_cuda:
             from . import _native as nat
