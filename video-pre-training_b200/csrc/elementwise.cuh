@@ -417,12 +417,7 @@ extern "C" int vpt_affine_norm_zp(const void* in, const float* mr, const float* 
     VPT_CHECK(C % 8 == 0 && H > 0 && W > 0, "vpt_affine_norm_zp: need C %% 8 == 0");
     const long long items = (long long)(H + 1) * (W + 1) * (C / 8);
     const int bpg = vpt_norm_stat_parts((H + 1) * (W + 1), C);
-    static int fast_ok = -1;  // A/B knob: VPT_NORM_ROWS=0 selects the first (index-arithmetic heavy) kernel
-    if (fast_ok < 0) {
-        const char* e = getenv("VPT_NORM_ROWS");
-        fast_ok = (e && e[0] == '0') ? 0 : 1;
-    }
-    const bool fast = fast_ok && C / 8 <= 256;
+    const bool fast = C / 8 <= 256;  // one channel vector per thread; wider rows fall back to the generic kernel
     for (long long g0 = 0; g0 < F; g0 += 65535) {
         const long long gn = (F - g0 < 65535) ? (F - g0) : 65535;
         dim3 grid(bpg, (unsigned)gn);

@@ -47,10 +47,6 @@ struct GemmParams {
     // weight-gradient mode (kWgrad): out[split][m][tap*N + n] = sum over this split's K rows of A[k][m] * B[k + tap_shift[tap]][n]
     // (both operands MN-major: A is [K rows][M], B is [K rows][N] in memory)
     int ntaps, k_splits, k_iters_split;
-    // a_cin > 0: operand roles swapped for a conv weight gradient -- A = layer input (rows m = tap*a_cin + ci, every 64-row TMA box of
-    // the A tile is read at ITS tap's row shift), B = output gradient; the result is stored transposed so that the caller still
-    // sees out[co][tap*a_cin + ci].  (M = Cout = 192 would fill 1.5 of 2 row tiles; 9*Cin rows fill 13.5 of 14.)
-    int a_cin, a_taps;
     int tap_shift[9];
     long long split_stride;
 };
@@ -144,20 +140,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_expect_tx(&full_bar[stage], kStageBytesA + stage_bytes_b);
                     uint8_t* sa = smem_a + (size_t)stage * kStageBytesA;
                     uint8_t* sb = smem_b + (size_t)stage * stage_bytes_b;
-                    if (kWgrad && p.a_cin > 0) {
-#pragma unroll
-                        for (int bx = 0; bx < 2; ++bx) {
-                            const int mm = m0 + 64 * bx, atap = mm / p.a_cin;
-                            if (atap < p.a_taps)
-                                tma_load_2d(sa + bx * 8192, &tmA, &full_bar[stage], mm - atap * p.a_cin, it * kBlockK + p.tap_shift[atap]);
-                            else  // rows past the last tap: a box outside the tensor = zeros (and the expected byte count stays the same)
-                                tma_load_2d(sa + bx * 8192, &tmA, &full_bar[stage], p.a_cin, it * kBlockK);
-                        }
-                        for (int bx = 0; bx < p.block_n / 64; ++bx)
-                            tma_load_2d(sb + bx * 8192, &tmB, &full_bar[stage], n0 + bx * 64, it * kBlockK);
-                        advance(stage, phase, p.num_stages);
-                        continue;
-                    }
                     if (kWgrad) {
                         tma_load_2d(sa, &tmA, &full_bar[stage], m0, it * kBlockK);
                         tma_load_2d(sa + 8192, &tmA, &full_bar[stage], m0 + 64, it * kBlockK);
@@ -350,14 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.out_f32) {
                     float* op = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ld_out + nb;
                     if (kWgrad) op += (size_t)split * p.split_stride + (size_t)tap * p.N;
-                    if (kWgrad && p.a_cin > 0) {
-                        // transposed store: this thread's row m = tap*Cin + ci is a COLUMN of out[co][tap*Cin + ci]; the 32 lanes of
-                        // the warp hold consecutive m, so every store instruction still writes 128 contiguous bytes
-                        float* ot = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)nb * p.ld_out + m;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < lim) ot[(size_t)j * p.ld_out] = v[j];
-                    } else if (full && (p.ld_out & 3) == 0) {
+                    if (full && (p.ld_out & 3) == 0) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
                             reinterpret_cast<float4*>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -640,33 +615,23 @@ struct WgradPlan {
     int block_n, n_tiles, m_tiles, k_iters, splits, k_iters_split;
 };
 
-static int g_wgrad_swap = -1;  // A/B knob: VPT_WGRAD_SWAP=0 keeps M = Cout for conv weight gradients
-static bool wgrad_swapped(int N, int ntaps) {
-    if (g_wgrad_swap < 0) {
-        const char* e = getenv("VPT_WGRAD_SWAP");
-        g_wgrad_swap = (e && e[0] == '0') ? 0 : 1;
-    }
-    return g_wgrad_swap && ntaps > 1 && N % 64 == 0;
-}
-
-// GEMM dimensions (Mk rows x Nk columns per "tap column") -> tiling and K split
-static WgradPlan wgrad_plan_mn(int Mk, int Nk, int ncols, long long R) {
+static WgradPlan wgrad_plan(int M, int N, int ntaps, long long R) {
     WgradPlan w;
     // whole 64-column TMA boxes; among 256 / 192 / 128 pick the width that pads N the least (N = 384 -> 2 x 192, not 256 + 128)
-    if (Nk <= 256) {
-        w.block_n = (Nk + 63) / 64 * 64;
+    if (N <= 256) {
+        w.block_n = (N + 63) / 64 * 64;
     } else {
-        int best = 256, best_pad = (Nk + 255) / 256 * 256 - Nk;
+        int best = 256, best_pad = (N + 255) / 256 * 256 - N;
         for (int bn = 192; bn >= 128; bn -= 64) {
-            const int pad = (Nk + bn - 1) / bn * bn - Nk;
+            const int pad = (N + bn - 1) / bn * bn - N;
             if (pad < best_pad) { best = bn; best_pad = pad; }
         }
         w.block_n = best;
     }
-    w.n_tiles = (Nk + w.block_n - 1) / w.block_n;
-    w.m_tiles = (Mk + kBlockM - 1) / kBlockM;
+    w.n_tiles = (N + w.block_n - 1) / w.block_n;
+    w.m_tiles = (M + kBlockM - 1) / kBlockM;
     w.k_iters = (int)((R + kBlockK - 1) / kBlockK);
-    const int tiles = w.m_tiles * w.n_tiles * ncols;
+    const int tiles = w.m_tiles * w.n_tiles * ntaps;
     int splits = (2 * num_sms() + tiles - 1) / tiles;  // ~2 work items per SM
     const int max_splits = w.k_iters / 8 > 0 ? w.k_iters / 8 : 1;  // at least 8 K iterations per item
     if (splits > max_splits) splits = max_splits;
@@ -675,11 +640,6 @@ static WgradPlan wgrad_plan_mn(int Mk, int Nk, int ncols, long long R) {
     w.k_iters_split = (w.k_iters + splits - 1) / splits;
     w.splits = (w.k_iters + w.k_iters_split - 1) / w.k_iters_split;  // every split owns >= 1 iteration
     return w;
-}
-
-static WgradPlan wgrad_plan(int M, int N, int ntaps, long long R) {
-    if (wgrad_swapped(N, ntaps)) return wgrad_plan_mn(ntaps * N, M, 1, R);
-    return wgrad_plan_mn(M, N, ntaps, R);
 }
 
 // out[i] = sum_s part[s][i] in a fixed order; 4 floats per thread
@@ -715,17 +675,12 @@ extern "C" int vpt_wgrad_bf16(const void* a, int64_t lda, const void* b, int64_t
     const long long out_elems = (long long)M * N * ntaps;
     VPT_CHECK(w.splits == 1 || (workspace && workspace_bytes >= (int64_t)w.splits * out_elems * 4),
               "vpt_wgrad_bf16: workspace too small (%lld bytes, need %lld)", (long long)workspace_bytes, (long long)w.splits * out_elems * 4);
-    const bool swapped = wgrad_swapped(N, ntaps);
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.M = swapped ? ntaps * N : M;
-    p.N = swapped ? M : N;
-    p.K = (int)R;
+    p.M = M; p.N = N; p.K = (int)R;
     p.block_n = w.block_n; p.num_n_tiles = w.n_tiles; p.num_m_tiles = w.m_tiles;
     p.k_iters = w.k_iters; p.k_splits = w.splits; p.k_iters_split = w.k_iters_split;
-    p.ntaps = swapped ? 1 : ntaps;
-    p.a_cin = swapped ? N : 0;
-    p.a_taps = swapped ? ntaps : 0;
+    p.ntaps = ntaps;
     for (int i = 0; i < ntaps; ++i) p.tap_shift[i] = shifts[i];
     p.cluster = 1;
     p.px_per_frame = 1; p.W = 1; p.H = 1; p.rows_per_group = 1;
@@ -739,14 +694,14 @@ extern "C" int vpt_wgrad_bf16(const void* a, int64_t lda, const void* b, int64_t
         cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)R};
         cuuint64_t strides[1] = {(cuuint64_t)lda * 2};
         cuuint32_t box[2] = {64, 64};
-        int r = make_tmap_bf16(swapped ? &tmB : &tmA, a, 2, dims, strides, box);
+        int r = make_tmap_bf16(&tmA, a, 2, dims, strides, box);
         if (r) return r;
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)R};
         cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
         cuuint32_t box[2] = {64, 64};
-        int r = make_tmap_bf16(swapped ? &tmA : &tmB, b, 2, dims, strides, box);
+        int r = make_tmap_bf16(&tmB, b, 2, dims, strides, box);
         if (r) return r;
     }
     const uint32_t stage_bytes = kStageBytesA + (uint32_t)p.block_n * kBlockK * 2;
@@ -760,7 +715,7 @@ extern "C" int vpt_wgrad_bf16(const void* a, int64_t lda, const void* b, int64_t
         VPT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int items = w.m_tiles * w.n_tiles * p.ntaps * w.splits;
+    const int items = w.m_tiles * w.n_tiles * ntaps * w.splits;
     const int grid = items < num_sms() ? items : num_sms();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
