@@ -97,3 +97,23 @@ def test_flat_bucket_clip_matches_torch():
     assert torch.allclose(total, total_ref) and total > 5.0
     for p, r in zip(params, ref):
         assert torch.allclose(p.grad, r.grad, rtol=1e-6, atol=1e-7)
+
+
+def test_emulation_mirrors_the_ops_api():
+    """The test-only emulation must expose every kernel-launching op of video_pre_training_b200.ops with the same parameter
+    names, so that host logic verified against it on CPU is the host logic that drives the kernels."""
+    import inspect
+
+    skip = {"require_cuda", "set_default_cluster", "gemm_stat_parts"}
+    missing, mismatched = [], []
+    for name, fn in vars(ops).items():
+        if name.startswith("_") or not inspect.isfunction(fn) or fn.__module__ != ops.__name__ or name in skip:
+            continue
+        emu = getattr(emu_ops, name, None)
+        if emu is None:
+            missing.append(name)
+            continue
+        if list(inspect.signature(fn).parameters) != list(inspect.signature(emu).parameters):
+            mismatched.append((name, list(inspect.signature(fn).parameters), list(inspect.signature(emu).parameters)))
+    assert not missing, f"ops without an emulation: {missing}"
+    assert not mismatched, mismatched

@@ -21,7 +21,7 @@ def oracle_grads(sd, cfg, img, first, state, actions):
     return loss.detach(), {k: v.grad for k, v in leaf.items()}, st
 
 
-def run_case(dev, B=2, T=8, chunks=2, seed=0):
+def run_case(dev, B=2, T=8, chunks=2, seed=0, reset_at=None):
     pol, sd, cfg = make_policy(small_kwargs())
     pol = pol.to(dev)
     g = torch.Generator().manual_seed(seed)
@@ -31,6 +31,8 @@ def run_case(dev, B=2, T=8, chunks=2, seed=0):
     for c in range(chunks):
         img = torch.randint(0, 256, (B, T, 32, 32, 3), dtype=torch.uint8, generator=g)
         first = torch.zeros(B, T, dtype=torch.bool)
+        if reset_at is not None and c == reset_at[0]:
+            first[reset_at[1], 0] = True  # episode boundary: this row must not see (or back-propagate into) its old memory
         actions = {"camera": torch.randint(0, 121, (B, T, 1), generator=g), "buttons": torch.randint(0, 8641, (B, T, 1), generator=g)}
         for p in pol.parameters():
             p.grad = None
@@ -76,7 +78,7 @@ def test_bc_backward_is_the_exact_gradient(emulated, exact):
     chain rule, the norm-fold algebra, the weight-layout round trips, the KV-memory detach and the loss scaling.  Tolerance:
     the folded forward differs from the oracle by ~1e-6, which flips the ReLU mask of an element that sits at zero once in a
     few million elements; one flip moves a frame's gradient by a few percent, everything else agrees to ~1e-6."""
-    out = run_case("cpu")
+    out = run_case("cpu") + run_case("cpu", chunks=3, seed=1, reset_at=(1, 1))  # second run: an episode reset in chunk 1, row 1
     check(out, tol_l2=5e-2)
     exact_params = 0
     for _, _, grads, grads_o in out:
