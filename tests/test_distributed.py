@@ -135,9 +135,18 @@ def _bc_worker(rank, world, port, q):
     lo, hi = parallel.shard_range(B, rank, world)
     with emulation():
         opt.zero_grad()
-        BCTrainer(pol).loss_and_grad(img[lo:hi], first[lo:hi], pol.initial_state(hi - lo), {k: v[lo:hi] for k, v in actions.items()})
+        shard = (img[lo:hi], first[lo:hi], pol.initial_state(hi - lo), {k: v[lo:hi] for k, v in actions.items()})
+        BCTrainer(pol).loss_and_grad(*shard)
         w = opt.reduce_gradients()                      # the step's single collective
         dp_grad = opt.flat_g.clone() / w                # (the 1/world lives in the Adam kernel)
+        # overlapped variant: the slice from the dense layer on is reduced while the ImpalaCNN backward still runs
+        split = opt.offset_of(pol.net.img_process.cnn.dense.norm.weight)
+        assert 0 < split < opt.n and opt.offset_of(named[0][1]) == 0
+        opt.zero_grad()
+        BCTrainer(pol).loss_and_grad(*shard, upper_grads_ready=lambda: opt.reduce_async(split, opt.n))
+        assert opt._pending is not None
+        opt.reduce_gradients()
+        assert opt._pending is None and torch.equal(opt.flat_g / w, dp_grad)
         if rank == 0:                                   # the same global batch in one process
             opt.zero_grad()
             BCTrainer(pol).loss_and_grad(img, first, pol.initial_state(B), actions)

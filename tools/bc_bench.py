@@ -21,6 +21,7 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--profile", action="store_true", help="per-GEMM timing of one step (tensor-core kernels only)")
+ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after the backward instead of overlapping the upper slice")
 ap.add_argument("--ops", action="store_true", help="per-op CUDA-event breakdown of one step (outer ops include the ops they call)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -39,6 +40,9 @@ actions = {"camera": torch.randint(0, 121, (B, T, 1), device="cuda", generator=g
 tr = BCTrainer(pol)
 opt = FlatAdamDP([p for n, p in pol.named_parameters() if not n.startswith("value_head")], lr=0.000181, weight_decay=0.039428)  # behavioural_cloning.py:38-39
 state = pol.initial_state(B)
+# everything from the dense layer on (98 % of the bucket) is final before the ImpalaCNN backward starts
+split = opt.offset_of(pol.net.img_process.cnn.dense.norm.weight)
+hook = None if a.no_overlap else (lambda: opt.reduce_async(split, opt.n))
 ev = lambda: torch.cuda.Event(enable_timing=True)
 
 
@@ -47,7 +51,7 @@ def step(timed=None):
     opt.zero_grad()
     if timed:
         timed[0].record()
-    loss, state = tr.loss_and_grad(img, first, state, actions)
+    loss, state = tr.loss_and_grad(img, first, state, actions, upper_grads_ready=hook)
     if timed:
         timed[1].record()
     opt.step()

@@ -169,7 +169,9 @@ class BCTrainer:
         return self._norm_bwd(du, x, mr, g32, 1, x.shape[1], (gam, ident), (bet, ident), add=add, relu_x=relu_x)
 
     # -- the step ---------------------------------------------------------------------------------------------------------
-    def loss_and_grad(self, img, first, state_in, actions):
+    def loss_and_grad(self, img, first, state_in, actions, upper_grads_ready=None):
+        """`upper_grads_ready()` is called once every gradient except those of `img_process.cnn.stacks.*` is final (the ImpalaCNN
+        backward, most of the step's time, is still to come): the hook for `FlatAdamDP.reduce_async`."""
         pol, net = self.policy, self.policy.net
         cfg = net.cfg
         wts = self._weights()
@@ -225,6 +227,8 @@ class BCTrainer:
         # ---------------- img_process.linear, dense ----------------
         dz = self._normlinear_bwd(dx, tape["xd"], tape["mr_d"], wts["linear_t"], "img_process.linear", P, relu_x=True)
         dcnn = self._dense_bwd(dz, tape, wts, P)
+        if upper_grads_ready is not None:
+            upper_grads_ready()
         # ---------------- ImpalaCNN, last stack to first ----------------
         self._cnn_bwd(dcnn, tape, wts, P)
         return loss, state_out
