@@ -128,3 +128,45 @@ def test_reset_equals_fresh():
 def test_flop_model_matches_survey():
     for w, gf in (("1x", 3.8213), ("2x", 15.0973), ("3x", 33.8278)):
         assert abs(O.forward_flops_per_frame(O.Cfg(**O.widths(w))) / 1e9 - gf) < 1e-3
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_gradient_matches_live_reference_autograd():
+    """The BC step's parity target is autograd through the oracle (tests/test_training.py); this pins that target itself: the
+    gradient of the BC loss (behavioural_cloning.py:101-123: -log-prob of the demonstrated action, KV memory detached between
+    chunks) through the unmodified reference equals the gradient through the oracle, parameter by parameter."""
+    import make_golden
+
+    pkw = refshim.policy_kwargs("2x", **refshim.TINY)
+    pol = refshim.make_reference_agent_policy(pkw)
+    make_golden.perturb(pol)
+    pol.train()  # as behavioural_cloning.py leaves it (no dropout / batch-norm in these models: same function)
+    sd = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    cfg = O.Cfg(**pkw)
+    B, T = 2, 8
+    g = torch.Generator().manual_seed(3)
+    st_r, st_o = pol.initial_state(B), O.initial_state(cfg, B)
+    for ci in range(2):
+        img = torch.randint(0, 256, (B, T, 32, 32, 3), dtype=torch.uint8, generator=g)
+        first = torch.zeros(B, T, dtype=torch.bool)
+        actions = {"camera": torch.randint(0, 121, (B, T, 1), generator=g), "buttons": torch.randint(0, 8641, (B, T, 1), generator=g)}
+        for p in pol.parameters():
+            p.grad = None
+        (pd, _, _), st_r = pol({"img": img}, first, st_r)
+        loss_r = -pol.pi_head.logprob(actions, pd).mean()
+        loss_r.backward()
+        st_r = [(m, (k.detach(), v.detach())) for (m, (k, v)) in st_r]  # tree_map(lambda x: x.detach(), ...) :111
+        leaf = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+        (pd_o, _, _), st_o = O.agent_policy_forward(leaf, cfg, img, first, st_o)
+        loss_o = -O.logprob(pd_o, actions).mean()
+        loss_o.backward()
+        st_o = [(m, (k.detach(), v.detach())) for (m, (k, v)) in st_o]
+        assert torch.equal(loss_r.detach(), loss_o.detach())
+        n_checked = 0
+        for name, p in pol.named_parameters():
+            if p.grad is None:
+                assert leaf[name].grad is None, name  # value head: untouched by the BC loss in both
+                continue
+            assert torch.allclose(p.grad, leaf[name].grad, rtol=1e-5, atol=1e-8), name
+            n_checked += 1
+        assert n_checked > 80
