@@ -122,3 +122,27 @@ def test_conv3d_kernel():
         assert (got.float().cpu() - ref.float()).abs().max() < 2e-2 and torch.allclose(gmr.cpu(), rmr, rtol=2e-3, atol=2e-3)
         gc = got.cpu()
         assert (gc[:, -1] == 0).all() and (gc[:, :, -1] == 0).all()
+
+
+def test_idm_agent_predict_actions_emulated(emulated, monkeypatch):
+    """inverse_dynamics_model.py:75-95 mirror: frames in, MineRL action dict out (host glue around InverseActionPolicy.predict)."""
+    import numpy as np
+
+    from video_pre_training_b200 import agent as A
+
+    monkeypatch.setattr(A, "AGENT_RESOLUTION", (32, 32))  # the small test model sees 32x32 frames: no resize on the CPU
+    kw = vpt_b200.idm_net_kwargs(**SMALL_IDM)
+    torch.manual_seed(0)
+    ag = vpt_b200.IDMAgent(kw, dict(temperature=2.0), device="cpu")
+    frames = np.random.default_rng(0).integers(0, 256, (8, 32, 32, 3), dtype=np.uint8)
+    act = ag.predict_actions(frames)
+    assert set(act) == set(A.BUTTONS) | {"camera"}
+    assert act["camera"].shape == (1, 8, 2) and act["attack"].shape == (1, 8) and set(np.unique(act["attack"])) <= {0, 1}
+    assert np.all(np.abs(act["camera"]) <= 10.0)
+    # same heads through the policy API
+    ac, _, _ = ag.policy.predict({"img": torch.from_numpy(frames)[None]}, first=torch.zeros(1, 8, dtype=torch.bool),
+                                 state_in=ag.policy.initial_state(1), deterministic=True)
+    assert np.array_equal(act["attack"], ac["buttons"][..., A.BUTTONS.index("attack")].numpy())
+    assert np.allclose(act["camera"], ag.codec.undiscretize_camera(ac["camera"].numpy()))
+    ag.reset()
+    assert ag.hidden_state[0][0] is None

@@ -259,3 +259,51 @@ class MineRLAgent:
         act = self._step if self._graphed else self.policy.act
         agent_action, self.hidden_state, _ = act(agent_input, self._dummy_first, self.hidden_state, stochastic=True)
         return self._agent_action_to_env(agent_action)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# IDMAgent
+# ---------------------------------------------------------------------------------------------------------------------
+class IDMAgent:
+    """inverse_dynamics_model.py:20-95 without the gym / cv2 dependency: the inverse dynamics model labelling video frames with
+    actions.  The IDM's action space is already factored (IDMActionMapping is the identity, lib/action_mapping.py:102-108), so the
+    env action is `ActionCodec.policy2env` of the arg-max heads."""
+
+    def __init__(self, idm_net_kwargs, pi_head_kwargs, device=None):
+        from .types import idm_action_space
+
+        self.device = torch.device(device or "cuda")
+        self.codec = ActionCodec(**ACTION_TRANSFORMER_KWARGS)
+        self.policy = _policy.InverseActionPolicy(idm_action_space(), pi_head_kwargs, idm_net_kwargs).to(self.device)
+        self.hidden_state = self.policy.initial_state(1)
+
+    def load_weights(self, path):
+        """inverse_dynamics_model.py:45-48."""
+        from .checkpoint import load_weights
+        load_weights(self.policy, path, map_location=self.device)
+        self.reset()
+
+    def reset(self):
+        """inverse_dynamics_model.py:50-52."""
+        self.hidden_state = self.policy.initial_state(1)
+
+    def _video_obs_to_agent(self, video_frames):
+        """inverse_dynamics_model.py:54-59: (N, H, W, 3) uint8 frames -> {"img": (1, N, 128, 128, 3)} on the device (GPU resize)."""
+        frames = video_frames if isinstance(video_frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(video_frames))
+        frames = frames.to(self.device)
+        if tuple(frames.shape[1:3]) != (AGENT_RESOLUTION[1], AGENT_RESOLUTION[0]):
+            frames = resize_frames(frames, AGENT_RESOLUTION)
+        return {"img": frames[None]}
+
+    def _agent_action_to_env(self, agent_action):
+        """inverse_dynamics_model.py:61-73."""
+        action = {k: v.cpu().numpy() for k, v in agent_action.items()}
+        return self.codec.policy2env(action)
+
+    def predict_actions(self, video_frames):
+        """inverse_dynamics_model.py:75-95: deterministic action labels for a clip; every head has shape (1, N, ...)."""
+        agent_input = self._video_obs_to_agent(video_frames)
+        n = agent_input["img"].shape[1]
+        dummy_first = torch.zeros((1, n), dtype=torch.bool, device=self.device)  # the unmasked IDM attention ignores `first`
+        predicted, self.hidden_state, _ = self.policy.predict(agent_input, first=dummy_first, state_in=self.hidden_state, deterministic=True)
+        return self._agent_action_to_env(predicted)
