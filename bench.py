@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--timesteps", type=int, default=128)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra blocks (gpu_eager_baseline, configs, bc, sample_agreement)")
+    ap.add_argument("--bc-width", default="3x", choices=["1x", "2x", "3x"])
+    ap.add_argument("--bc-batch", type=int, default=16)
+    ap.add_argument("--bc-steps", type=int, default=4)
     return ap.parse_args()
 
 
@@ -166,12 +170,272 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# extra blocks of the JSON line: every number that used to be prose in DESIGN.md
+# ------------------------------------------------------------------------------------------------------------------
+def _free():
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def _event_ms(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def gpu_eager_baseline(width, dev, B=4, T=128, seconds=6.0):
+    """The honest GPU bar (SURVEY 8d / BASELINE.md 4): the reference ALGORITHM run eagerly by PyTorch on the same B200 -- the oracle
+    port (same torch ops in the same order as lib/policy.py; the reference itself cannot travel to the GPU box) dispatched to
+    cuDNN / cuBLAS / ATen, fp32 with TF32 off and on.  B x T = 128 x 128 does not fit (8 MiB of fp32 per frame for the first conv
+    alone), so it runs B sequences of T frames with the KV memory full; per-frame cost is batch independent."""
+    import vpt_oracle as O
+    import vpt_b200
+
+    kw = vpt_b200.policy_kwargs(width)
+    torch.manual_seed(0)
+    pol = vpt_b200.MinecraftAgentPolicy(vpt_b200.minecraft_action_space(), kw, vpt_b200.PI_HEAD_KWARGS)
+    sd = {k: v.detach().to(dev) for k, v in pol.state_dict().items()}
+    del pol
+    cfg = O.Cfg(**kw)
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, generator=g).to(dev)
+    first = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    out = {"kind": "port", "sample": f"oracle/vpt_oracle.py on cuda (torch {torch.__version__} eager: cuDNN/cuBLAS/ATen), {width} width, fp32, "
+                                      f"B={B} T={T} with full KV memory, best of the passes that fit in {seconds:.0f} s per mode",
+           "unit": "frames/s"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        with torch.device(dev), torch.no_grad():
+            for name, tf32 in (("fp32_tf32_off", False), ("fp32_tf32_on", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                st = O.initial_state(cfg, B)
+                for _ in range(2):  # warm-up (cuDNN heuristics) + fills the KV memory
+                    _, st = O.agent_policy_forward(sd, cfg, img, first, st)
+                torch.cuda.synchronize()
+                best, t_begin = None, time.perf_counter()
+                while time.perf_counter() - t_begin < seconds:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    (pd, v, _), st = O.agent_policy_forward(sd, cfg, img, first, st)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1)
+                    best = ms if best is None else min(best, ms)
+                out[name] = B * T / (best / 1000.0)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del sd, img
+    _free()
+    return out
+
+
+def sample_agreement(pol, kw, dev, B=2, T=24, seed=1234):
+    """End-to-end agreement of the SAMPLED action indices with the oracle (north_star: 'bit-exact on sampled action indices under a
+    fixed seed'; lib/action_head.py:195-207): the CUDA policy (bf16 operands) and the fp32 oracle (host CPU) see the same frames, the
+    same weights and the same uniforms (the CUDA Philox stream after torch.manual_seed(seed), drawn camera-then-buttons like
+    DictActionHead.sample).  The sampler itself is bit exact given logits (tests/test_gpu_policy.py); a mismatch here is a Gumbel
+    arg-max whose top-two gap is below the bf16 logit error."""
+    import vpt_oracle as O
+
+    sd = {k: v.detach().cpu().float() for k, v in pol.state_dict().items()}
+    cfg = O.Cfg(**kw)
+    g = torch.Generator().manual_seed(7)
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, generator=g)
+    first = torch.zeros(B, T, dtype=torch.bool)
+    (pd, _, _), _ = pol({"img": img.to(dev)}, first.to(dev), pol.initial_state(B))
+    torch.manual_seed(seed)
+    ac = pol.sample(pd)
+    ac_det = pol.sample(pd, deterministic=True)
+    torch.manual_seed(seed)  # replay the same Philox stream for the oracle
+    us = {name: torch.rand_like(pd[name].contiguous()).cpu() for name in pd}
+    nthr = torch.get_num_threads()
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    with torch.no_grad():
+        (pd_o, _, _), _ = O.agent_policy_forward(sd, cfg, img, first, O.initial_state(cfg, B))
+    torch.set_num_threads(nthr)
+    out = {"frames": B * T, "seed": seed, "rng": "CUDA Philox, torch.manual_seed(seed), camera then buttons"}
+    for name in pd:
+        so = O.gumbel_sample(pd_o[name], us[name])
+        do = torch.argmax(pd_o[name], dim=-1)
+        n = so.numel()
+        out[name] = {"stochastic_agree": int((ac[name].cpu().view_as(so) == so).sum()) / n,
+                     "deterministic_agree": int((ac_det[name].cpu().view_as(do) == do).sum()) / n,
+                     "logprob_max_rel_err": float(((pd[name].cpu() - pd_o[name]).abs() / pd_o[name].abs()).max())}
+    return out
+
+
+def config_blocks(dev, pk):
+    """BASELINE configs C2 (1x, B=64, T=128), C5 (IDM 4x, B=64, T=128) and the f-1 rollout step, each with its own roofline fraction."""
+    import vpt_b200
+    from video_pre_training_b200 import _native as nat
+
+    out = {}
+    # ---- C2: 1x width, B=64, T=128, bf16 inference-only forward
+    kw = vpt_b200.policy_kwargs("1x")
+    torch.manual_seed(0)
+    pol = vpt_b200.MinecraftAgentPolicy(vpt_b200.minecraft_action_space(), kw, vpt_b200.PI_HEAD_KWARGS).to(dev)
+    B, T = 64, 128
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, device=dev)
+    first = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    box = {"st": pol.initial_state(B)}
+
+    def step_c2():
+        (_, _, _), box["st"] = pol({"img": img}, first, box["st"])
+
+    ms = _event_ms(step_c2, 5, 3)
+    fl = pol.net.cfg.forward_flops_per_frame()
+    fps = B * T / ms * 1000.0
+    out["C2_1x_B64_T128"] = {"frames_per_s": fps, "ms_per_step": ms, "gflop_per_frame": fl / 1e9,
+                             "frac_of_flop_roofline": fps * fl / 1e12 / pk["tflops"]}
+    nat.device_check()
+    del pol, img, box
+    _free()
+    # ---- C5: IDM 4x, B=64, T=128 (bidirectional attention, conv3d pre-stage)
+    ikw = vpt_b200.idm_net_kwargs()
+    torch.manual_seed(0)
+    idm = vpt_b200.InverseActionPolicy(vpt_b200.idm_action_space(), dict(temperature=2.0), ikw).to(dev)
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, device=dev)
+
+    def step_c5():
+        idm.predict({"img": img}, first=first, state_in=idm.initial_state(B))
+
+    ms = _event_ms(step_c5, 2, 1)
+    fl = idm.net.cfg.forward_flops_per_frame(idm._heads_prepared()["ntot"])  # 68.59 GFLOP (SURVEY 8d: 68.62 incl. the discarded lastlayer)
+    fps = B * T / ms * 1000.0
+    out["C5_idm4x_B64_T128"] = {"frames_per_s": fps, "ms_per_step": ms, "gflop_per_frame": fl / 1e9,
+                                "frac_of_flop_roofline": fps * fl / 1e12 / pk["tflops"]}
+    nat.device_check()
+    del idm, img
+    _free()
+    # ---- f-1: rollout step, 2x, B=1, T=1 (agent.py:190-206): one CUDA graph per step; bound = streaming the bf16 weights once
+    kw = vpt_b200.policy_kwargs("2x")
+    torch.manual_seed(0)
+    pol = vpt_b200.MinecraftAgentPolicy(vpt_b200.minecraft_action_space(), kw, vpt_b200.PI_HEAD_KWARGS).to(dev)
+    step = pol.make_graphed_act(1)
+    img1 = torch.randint(0, 256, (1, 128, 128, 3), dtype=torch.uint8, device=dev)
+    first1 = torch.zeros(1, dtype=torch.bool, device=dev)
+    box = {"st": pol.initial_state(1)}
+
+    def step_f1():
+        ac, box["st"], _ = step({"img": img1}, first1, box["st"])
+        return ac
+
+    for _ in range(5):
+        step_f1()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 200
+    for _ in range(n):
+        ac = step_f1()
+        ac["buttons"].cpu()  # the env needs the action on the host every step
+    wall_ms = (time.perf_counter() - t0) / n * 1000.0
+    dev_ms = _event_ms(step_f1, 200, 5)
+    wbytes = sum(p.numel() for p in pol.parameters()) * 2
+    bound_ms = wbytes / (pk["hbm"] * 1e9) * 1000.0
+    out["f1_rollout_2x_B1_T1"] = {"ms_per_step_device": dev_ms, "ms_per_step_wall_with_d2h": wall_ms, "weight_bytes_bf16": wbytes,
+                                  "hbm_bound_ms": bound_ms, "frac_of_hbm_bound": bound_ms / dev_ms}
+    nat.device_check()
+    del pol, step, box
+    _free()
+    return out
+
+
+def bc_block(args, dev, world, rank, pk):
+    """BASELINE configs[3]: BC fine-tune step (fwd + hand-written bwd + ONE NCCL all-reduce over the flat fp32 gradient bucket + fused
+    Adam) at `world` ranks, B clips per GPU, T=128 (behavioural_cloning.py:101-123).  The only path with a collective."""
+    import torch.distributed as dist
+    import vpt_b200
+    from video_pre_training_b200 import _native as nat
+    from video_pre_training_b200.parallel import FlatAdamDP
+    from video_pre_training_b200.training import BCTrainer
+
+    kw = vpt_b200.policy_kwargs(args.bc_width)
+    torch.manual_seed(0)
+    pol = vpt_b200.MinecraftAgentPolicy(vpt_b200.minecraft_action_space(), kw, vpt_b200.PI_HEAD_KWARGS).to(dev)
+    B, T = args.bc_batch, 128
+    g = torch.Generator(device=dev).manual_seed(rank)
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, device=dev, generator=g)
+    first = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    actions = {"camera": torch.randint(0, 121, (B, T, 1), device=dev, generator=g),
+               "buttons": torch.randint(0, 8641, (B, T, 1), device=dev, generator=g)}
+    tr = BCTrainer(pol)
+    opt = FlatAdamDP([p for n, p in pol.named_parameters() if not n.startswith("value_head")], lr=0.000181, weight_decay=0.039428)
+    split = opt.offset_of(pol.net.img_process.cnn.dense.norm.weight)
+    hook = lambda: opt.reduce_async(split, opt.n)
+    box = {"st": pol.initial_state(B)}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(marks=None):
+        opt.zero_grad()
+        if marks:
+            marks[0].record()
+        loss, box["st"] = tr.loss_and_grad(img, first, box["st"], actions, upper_grads_ready=hook)
+        if marks:
+            marks[1].record()
+        opt.step()
+        if marks:
+            marks[2].record()
+        return loss
+
+    losses = [float(step()) for _ in range(2)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    marks = [(ev(), ev(), ev()) for _ in range(args.bc_steps)]
+    for m in marks:
+        losses.append(step(m))
+    torch.cuda.synchronize()
+    nat.device_check()
+    t = torch.tensor([marks[0][0].elapsed_time(marks[-1][2]) / args.bc_steps,
+                      sum(m[0].elapsed_time(m[1]) for m in marks) / args.bc_steps,
+                      sum(m[1].elapsed_time(m[2]) for m in marks) / args.bc_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, fb, ad = [float(x) for x in t.tolist()]
+    # the collective alone (not overlapped): bus bandwidth = 2 (N-1)/N x bytes / time
+    ar_ms, bus = None, None
+    if world > 1:
+        for _ in range(2):
+            dist.all_reduce(opt.flat_g)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(3):
+            dist.all_reduce(opt.flat_g)
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ar_ms = float(tt.item())
+        bus = 2.0 * (world - 1) / world * opt.n * 4 / (ar_ms / 1000.0) / 1e9
+    fl = 3.0 * pol.net.cfg.forward_flops_per_frame()  # SURVEY 8d: training step ~ 3x forward
+    fps = world * B * T / ms * 1000.0
+    res = {"workload": f"BC fine-tune step {args.bc_width}, B={B}/GPU T={T}, fwd + bwd + all-reduce(fp32 flat bucket) + Adam, x{world} GPU",
+           "ms_per_step": ms, "frames_per_s": fps, "fwd_bwd_ms": fb, "exposed_allreduce_plus_adam_ms": ad,
+           "allreduce_alone_ms": ar_ms, "nccl_bus_gb_s": bus, "gradient_bucket_bytes": opt.n * 4,
+           "frac_of_flop_roofline": (fps / world) * fl / 1e12 / pk["tflops"], "gflop_per_frame": fl / 1e9,
+           "loss_first_last": [float(losses[0]), float(losses[-1])]}
+    del pol, tr, opt, img, box
+    _free()
+    return res
+
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
 
     import vpt_b200
-    import vpt_oracle as O
     from video_pre_training_b200 import _native as nat
     from video_pre_training_b200 import ops
 
@@ -238,8 +502,7 @@ def run_ours(args):
     conv_fl = sum(f for _, _, f, k, _ in prof if k == "conv")
     pk = peaks()
     achieved = g_fl / (g_ms / 1000.0) / 1e12
-    cfg = O.Cfg(**kw)
-    flops_frame = O.forward_flops_per_frame(cfg)
+    flops_frame = pol.net.cfg.forward_flops_per_frame()  # product-side FLOP model (policy.NetConfig), SURVEY 8d
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                 "traffic": TRAFFIC_NCU, "kernel": "conv3x3_zp_kernel + gemm_tc_kernel (tcgen05 implicit-GEMM conv3x3 / linear)",
                 "peak_source": pk["source"],
@@ -276,6 +539,16 @@ def run_ours(args):
            "h2d_bytes_per_step": host_img.numel() + host_first.numel(), "d2h_bytes_per_step": d2h,
            "call": "HostFramePipe (pinned host frames -> device, double buffered) + MinecraftAgentPolicy.forward(obs, first, state) + sample(); sampled actions + vpred read back to the host every step"}
 
+    extras = {}
+    if not args.no_extras:
+        if rank == 0 and world == 1:
+            extras["sample_agreement"] = sample_agreement(pol, kw, dev)
+        del pol, state, state2, img, host_img, pipe, pd, vpred, ac, res, d_img
+        _free()
+        if rank == 0 and world == 1:
+            extras["gpu_eager_baseline"] = gpu_eager_baseline(args.width, dev)
+            extras["configs"] = config_blocks(dev, pk)
+        extras["bc"] = bc_block(args, dev, world, rank, pk)  # every rank: the one path with a collective
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_fps(args.width, args.cpu_baseline_seconds)
@@ -288,6 +561,7 @@ def run_ours(args):
                           "global_batch": world * B, "seq_len": T, "parallelism": f"batch-sharded x{world}, no collective",
                           "l2_policy": "inputs (805 MB u8 frames/step) exceed the 126 MB L2; no explicit flush"},
                "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        out.update(extras)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -30,7 +30,7 @@ extern "C" {
 #define VPT_ERR_CUDA (-2)   /* a CUDA runtime / driver call failed */
 #define VPT_ERR_DEVICE (-3) /* a kernel recorded a device-side protocol error (watchdog) */
 
-#define VPT_ABI_VERSION 1
+#define VPT_ABI_VERSION 2
 
 const char* vpt_last_error(void);
 int vpt_abi_version(void);
@@ -126,11 +126,16 @@ int vpt_conv_zp_stat_parts(int32_t Cout);
  * (lib/policy.py:39-45, lib/util.py:79-81 with bias, lib/impala_cnn.py:115-117).
  *   img  u8   [F][H][W][3]      w  fp32 [C0][27] ordered (ky, kx, c), already divided by 255
  *   out  bf16 [F][H/2][W/2][C0] (zp=0) or ZP [F][H/2+1][W/2+1][C0] (zp=1)
- *   stat_part float2 [F][(H/16)*(W/16)]   (H, W multiples of 16; C0 in {64,128,192,256})
+ *   stat_part float2 [F][vpt_firstconv_stat_parts(F, H, W, C0)]   (H, W multiples of 16; C0 in {64,128,192,256})
+ * Two kernels: for W in {32, 64, 128} with H*W <= 16384 the tcgen05 kernel (csrc/firstconv_tc.cuh: operand-swapped implicit GEMM,
+ * thread = channel, 3x3/2 max in registers; its partials are per (row band, column half, CHANNEL): partial index
+ * (band*2 + half)*C0 + c, so per-channel sums are available to the caller); otherwise the mma.sync kernel (csrc/firstconv.cuh,
+ * (H/16)*(W/16) partials per frame).  vpt_set_firstconv_mode(0) forces the mma.sync kernel (A/B knob).
  * -------------------------------------------------------------------------------------------------------- */
 int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part,
                        int32_t F, int32_t H, int32_t W, int32_t C0, int32_t zp, void* stream);
-int vpt_firstconv_stat_parts(int32_t H, int32_t W);
+int vpt_firstconv_stat_parts(int32_t F, int32_t H, int32_t W, int32_t C0);
+int vpt_set_firstconv_mode(int32_t mode);
 
 /* IDM temporal pre-stage (lib/policy.py:394-403 + :39-45): u8 -> /255 -> Conv3d(3 -> C, kernel (5,1,1), pad (2,0,0)) + bias -> ReLU,
  * per sample over its T frames (zero padded in time at the chunk ends, like the reference's per-sample loop).

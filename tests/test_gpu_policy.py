@@ -189,6 +189,29 @@ def test_graphed_act_matches_eager_and_logit_mask():
     nat.device_check()
 
 
+def test_graphed_act_follows_weight_changes():
+    """a captured rollout graph holds raw pointers to the kernel-layout weights; after load_state_dict / an
+    optimizer step it must re-layout and re-capture instead of replaying stale (or freed) weights."""
+    pol, sd, cfg = make_policy(small_kwargs())
+    pol = pol.to(DEV)
+    B = 2
+    step = pol.make_graphed_act(B)
+    g = torch.Generator().manual_seed(6)
+    img = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+    first = torch.zeros(B, dtype=torch.bool, device=DEV)
+    _, _, res0 = step({"img": img}, first, pol.initial_state(B), stochastic=False, return_pd=True)
+    pd0 = res0["pd"]["buttons"].clone()
+    pol2, sd2, _ = make_policy(small_kwargs(), seed=11)
+    pol.load_state_dict(sd2)                      # in-place copy_: same storage, new version counters
+    junk = [torch.randn(1 << 20, device=DEV) for _ in range(8)]  # recycle freed allocator blocks
+    _, _, res_e = pol.act({"img": img}, first, pol.initial_state(B), stochastic=False, return_pd=True)
+    _, _, res_g = step({"img": img}, first, pol.initial_state(B), stochastic=False, return_pd=True)
+    assert torch.equal(res_e["pd"]["buttons"], res_g["pd"]["buttons"])
+    assert not torch.equal(pd0, res_g["pd"]["buttons"])
+    del junk
+    nat.device_check()
+
+
 def test_bench_workload_128x128_rows_match_oracle():
     """The exact bench.py workload (2x width, B=128, T=128 = 16384 frames per chunk, 8 CNN sub-chunks of 2048 frames): two of
     the 128 sequences are followed by the CPU oracle; rows in different CNN sub-chunks must behave identically."""

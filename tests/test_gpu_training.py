@@ -217,6 +217,49 @@ def test_bc_step_matches_emulated_step_and_oracle_direction():
         assert c > 0.85, (n, c)
 
 
+def test_cuda_backward_matches_autograd_at_the_taped_operating_point():
+    """The tight pin of the CUDA backward (ADVICE): the CUDA forward's taped activations are fed into the
+    forced torch-autograd replica (tests/forced_replica.py: fp32 layers from the parameters, values and ReLU / max-pool masks
+    forced from the tape, on the same GPU with TF32 off), so the comparison isolates the backward kernels -- dgrad / wgrad with bf16
+    operands, norm / pool / attention / softmax backward -- from forward mask flips.  Per-parameter rel-L2 < 2e-2."""
+    from forced_replica import forced_loss
+
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        for kw, B, T, seed in [(small_kwargs(), 2, 8, 0), (small_kwargs(timesteps=24, attention_memory_size=40), 3, 24, 3)]:
+            pol, sd, cfg = make_policy(kw, seed=seed)
+            g = torch.Generator().manual_seed(seed)
+            img = torch.randint(0, 256, (B, T, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+            first = torch.zeros(B, T, dtype=torch.bool, device=DEV)
+            actions = {"camera": torch.randint(0, 121, (B, T, 1), generator=g).to(DEV), "buttons": torch.randint(0, 8641, (B, T, 1), generator=g).to(DEV)}
+            pol = pol.to(DEV)
+            tr = BCTrainer(pol)
+            tr.keep_tape = True
+            state = pol.initial_state(B)
+            if seed:  # second case: a filled KV memory (detached constants in the backward) and a mid-batch episode start
+                (_, _, _), state = pol({"img": img}, first, state)
+                first = first.clone()
+                first[1, 0] = True
+            loss, _ = tr.loss_and_grad(img, first, state, actions)
+            nat.device_check()
+            leaf = {k: v.to(DEV).clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+            lf = forced_loss(leaf, cfg, tr.last_tape, img, first, actions)
+            lf.backward()
+            assert abs(loss.item() - lf.item()) < 1e-3 * abs(lf.item()), (loss.item(), lf.item())
+            errs = {}
+            for n, p in pol.named_parameters():
+                if n.startswith("value_head"):
+                    assert p.grad is None
+                    continue
+                errs[n] = rel(p.grad, leaf[n].grad)
+            print(f"B={B} T={T}: worst rel-L2 vs forced autograd {max(errs.values()):.4f} ({max(errs, key=errs.get)})")
+            for n, e in errs.items():
+                assert e < 2e-2, (n, e)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
 def test_bc_training_reduces_the_loss():
     """A few full steps (forward, backward, flat-bucket Adam) on one fixed batch must drive the NLL down."""
     pol, _, _ = make_policy(small_kwargs())

@@ -126,3 +126,29 @@ def test_kv_memory_is_detached_between_steps(emulated):
     for mask, (k, v) in st:
         assert mask.dtype == torch.bool and not k.requires_grad and not v.requires_grad and k.dtype == torch.float32
         assert k.shape == (1, 8, 256)
+
+
+def test_backward_matches_autograd_at_the_taped_operating_point(emulated):
+    """The tight gradient pin: autograd through the FORCED replica (tests/forced_replica.py: every layer
+    recomputed in fp32 from the parameters, values and ReLU / pool masks taken from the forward's tape) against the hand-written
+    backward, with every bf16 rounding point active.  No mask can flip, so the bound is per parameter and tight."""
+    from forced_replica import forced_loss
+
+    pol, sd, cfg = make_policy(small_kwargs())
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (2, 8, 32, 32, 3), dtype=torch.uint8, generator=g)
+    first = torch.zeros(2, 8, dtype=torch.bool)
+    actions = {"camera": torch.randint(0, 121, (2, 8, 1), generator=g), "buttons": torch.randint(0, 8641, (2, 8, 1), generator=g)}
+    tr = BCTrainer(pol)
+    tr.keep_tape = True
+    loss, _ = tr.loss_and_grad(img, first, pol.initial_state(2), actions)
+    leaf = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    lf = forced_loss(leaf, cfg, tr.last_tape, img, first, actions)
+    lf.backward()
+    assert abs(loss.item() - lf.item()) < 1e-4 * abs(lf.item())
+    for n, p in pol.named_parameters():
+        if n.startswith("value_head"):
+            assert p.grad is None
+            continue
+        e = ((p.grad - leaf[n].grad).norm() / leaf[n].grad.norm()).item()
+        assert e < 2e-2, (n, e)

@@ -81,7 +81,8 @@ SIGNATURES = {
     "vpt_set_conv_swap_mode": (_I, [_I]),
     "vpt_debug_set": (_I, [_I, _I]),
     "vpt_firstconv_pool": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "vpt_firstconv_stat_parts": (_I, [_I, _I]),
+    "vpt_firstconv_stat_parts": (_I, [_I, _I, _I, _I]),
+    "vpt_set_firstconv_mode": (_I, [_I]),
     "vpt_conv3d_t5": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vpt_conv3d_stat_parts": (_I, [_I, _I, _I]),
     "vpt_maxpool3s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

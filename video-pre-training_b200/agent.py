@@ -223,6 +223,7 @@ class MineRLAgent:
         """agent.py:132-135."""
         from .checkpoint import load_weights
         load_weights(self.policy, path, map_location=self.device)
+        self._step = None  # a captured rollout graph belongs to the old weights (GraphedAct re-checks too)
         self.reset()
 
     def reset(self):
@@ -281,6 +282,7 @@ class IDMAgent:
         """inverse_dynamics_model.py:45-48."""
         from .checkpoint import load_weights
         load_weights(self.policy, path, map_location=self.device)
+        self._step = None  # a captured rollout graph belongs to the old weights (GraphedAct re-checks too)
         self.reset()
 
     def reset(self):

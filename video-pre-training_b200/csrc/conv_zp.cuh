@@ -25,6 +25,10 @@ namespace vpt {
 
 static int g_cz_pair = 1;
 static int g_cz_dbg = 0;
+static int g_cz_tma = 1;  // pair kernel: TMA-store epilogue (0 = per-thread global stores, the round-1 epilogue; A/B knob)
+
+constexpr int kCzStgChunk = kBlockM * 64;        // one staging buffer: 128 rows x 32 channels bf16 (64-byte rows, SWIZZLE_64B)
+constexpr int kCzStgBytes = 2 * 4 * kCzStgChunk; // 2 epilogue groups x up to 4 chunks
 
 constexpr int kCzThreads = 96 + 32 * kNumEpiWarps;  // 11 warps
 constexpr int kCzMaxBStages = 8;
@@ -36,6 +40,7 @@ struct ConvZpParams {
     int mt;               // 128-row sub-tiles per CTA tile (1 or 2)
     int a_box_rows, a_boxes, a_stage_bytes, b_stages;
     int dbg;              // experiment: 1 = epilogue skips its global stores, 2 = skips the whole epilogue body
+    int tma_epi;          // pair kernel: epilogue I/O through shared memory + TMA (output store, residual prefetch)
     long long num_m_tiles;
     const float* mr;
     const float* S1;
@@ -51,7 +56,8 @@ struct ConvZpParams {
 // of single-CTA UMMA) is halved for the weights.
 template <bool kPair>
 __global__ void __launch_bounds__(kCzThreads, 1)
-conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvZpParams p) {
+conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                  const __grid_constant__ CUtensorMap tmR, const ConvZpParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -61,14 +67,16 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool leader = (cta_rank == 0);
     uint8_t* smem_a = smem;                                        // 2 A-span stages
     uint8_t* smem_b = smem + 2 * (size_t)p.a_stage_bytes;          // b_stages weight tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_stages * b_stage_bytes);
+    uint8_t* smem_stage = smem_b + (size_t)p.b_stages * b_stage_bytes;  // tma_epi: output / residual staging (1024-aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + (p.tma_epi ? kCzStgBytes : 0));
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + 2;
     uint64_t* b_full = bars + 4;
     uint64_t* b_empty = bars + 4 + kCzMaxBStages;
     uint64_t* tmem_full_bar = bars + 4 + 2 * kCzMaxBStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* slot_ready = tmem_empty_bar + 2;  // [2 groups][4 chunks]: staging buffer free (and its residual tile landed)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(slot_ready + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,6 +84,11 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.tma_epi) {
+            tma_prefetch_desc(&tmO);
+            if (p.residual) tma_prefetch_desc(&tmR);
+        }
+        for (int i = 0; i < 8; ++i) mbar_init(&slot_ready[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
@@ -204,6 +217,147 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
         }
+    } else if (kPair && p.tma_epi) {
+        // ================= epilogue (warps 3..10), shared-memory staged: TMA store of the output, TMA prefetch of the residual ======
+        // Round-1 ncu: with per-thread 16-byte global stores / residual loads every epilogue instruction touches 32 different
+        // 128-byte lines (32 L1 wavefronts), on the pipe the UMMA operand fetch needs (l1tex lsu 34-60 %, tensor pipe 71-79 %).
+        // Here a group of 4 warps (128 rows) owns one 128 x 32-channel staging buffer per column chunk (64-byte rows, SWIZZLE_64B:
+        // conflict-free 16-byte accesses): the residual chunk of the NEXT tile is TMA-loaded into the buffer as soon as the
+        // previous store has drained it, the threads add it and overwrite it IN PLACE with the output, one thread issues the TMA
+        // store.  Per chunk: 8 shared-memory instructions of 4 wavefronts instead of 8 global ones of 32.
+        const int ew = warp - 3;
+        const int quarter = warp & 3;
+        const int grp = ew >> 2;  // column half
+        const int nchunks = p.block_n >> 5;
+        const int c_begin = grp == 0 ? 0 : (nchunks + 1) >> 1;
+        const int c_end = grp == 0 ? (nchunks + 1) >> 1 : nchunks;
+        const int P = p.num_n_tiles * 2;
+        const int r_local = quarter * 32 + lane;
+        const bool leader_t = ((ew & 3) == 0) && lane == 0;
+        uint8_t* stg = smem_stage + (size_t)grp * 4 * kCzStgChunk;
+        uint64_t* slot = slot_ready + grp * 4;
+        const uint32_t my_row = smem_u32(stg) + (uint32_t)r_local * 64u;
+        const uint32_t swz = (uint32_t)((r_local >> 1) & 3);
+        auto setup_slot = [&](int j, long long tile) {  // leader only: buffer j is free -> arm it for `tile`
+            if (tile >= num_tiles) return;
+            if (p.residual) {
+                const long long m_tile = tile / p.num_n_tiles;
+                const int n0 = (int)(tile % p.num_n_tiles) * p.block_n;
+                mbar_expect_tx(&slot[j], (uint32_t)kCzStgChunk);
+                tma_load_2d(stg + (size_t)j * kCzStgChunk, &tmR, &slot[j], n0 + (c_begin + j) * 32, (int)(m_tile * tile_rows + cta_row0));
+            } else {
+                mbar_arrive(&slot[j]);
+            }
+        };
+        if (leader_t)
+            for (int j = 0; j < c_end - c_begin; ++j) setup_slot(j, tile_begin);
+        int local = 0;
+        bool ok = true;
+        for (long long tile = tile_begin; tile < num_tiles && ok; tile += tile_step, ++local) {
+            const long long m_tile = tile / p.num_n_tiles;
+            const int n_tile = (int)(tile % p.num_n_tiles);
+            const int n0 = n_tile * p.block_n;
+            const int as = local & 1;
+            const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
+            const long long row0 = m_tile * tile_rows + cta_row0;
+            const long long q = row0 + r_local;
+            const bool row_ok = q < p.Q;
+            const long long f = q / p.FS;
+            const int r = (int)(q - f * p.FS);
+            const int y = r / p.Wp, x = r - y * p.Wp;
+            const bool interior = row_ok && (y < p.H) && (x < p.W);
+            float ga = 1.f, gb = 0.f;
+            if (p.mr != nullptr && interior) {
+                const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
+                ga = rstd;
+                gb = rstd * mean;
+            }
+            const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+            const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+            const int cls = interior ? cy * 3 + cx : 0;
+            const float* s1row = p.S1 ? p.S1 + (size_t)cls * p.N : nullptr;
+            const float* s2row = p.S2 ? p.S2 + (size_t)cls * p.N : nullptr;
+            float st_s = 0.f, st_ss = 0.f;
+            if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x410u))) break;
+            tc_fence_after();
+            for (int c = c_begin; c < c_end && ok; ++c) {
+                const int j = c - c_begin;
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + c * 32), acc);
+                tmem_ld_wait();
+                if (c == c_end - 1) {  // accumulator stage fully read: release it to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+                }
+                const int nb = n0 + c * 32;
+                float v[32];
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                    const float4 a1 = s1row ? __ldg(reinterpret_cast<const float4*>(s1row + nb) + qq) : make_float4(0, 0, 0, 0);
+                    const float4 a2 = s2row ? __ldg(reinterpret_cast<const float4*>(s2row + nb) + qq) : make_float4(0, 0, 0, 0);
+                    v[4 * qq + 0] = fmaf(ga, __uint_as_float(acc[4 * qq + 0]), fmaf(-gb, a1.x, a2.x));
+                    v[4 * qq + 1] = fmaf(ga, __uint_as_float(acc[4 * qq + 1]), fmaf(-gb, a1.y, a2.y));
+                    v[4 * qq + 2] = fmaf(ga, __uint_as_float(acc[4 * qq + 2]), fmaf(-gb, a1.z, a2.z));
+                    v[4 * qq + 3] = fmaf(ga, __uint_as_float(acc[4 * qq + 3]), fmaf(-gb, a1.w, a2.w));
+                }
+                if (p.relu == 1) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+                }
+                // the staging buffer is free (its previous store has drained) and, with a residual, holds this tile's residual chunk
+                if (!mbar_wait(&slot[j], (uint32_t)local & 1u, 0x420u)) asm volatile("trap;");  // (a break would desynchronise the named barrier)
+                const uint32_t brow = my_row + (uint32_t)j * kCzStgChunk;
+                if (p.residual != nullptr) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        uint4 rr;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(brow + (((uint32_t)qq ^ swz) << 4)));
+                        v[8 * qq + 0] += bf16_lo(rr.x); v[8 * qq + 1] += bf16_hi(rr.x);
+                        v[8 * qq + 2] += bf16_lo(rr.y); v[8 * qq + 3] += bf16_hi(rr.y);
+                        v[8 * qq + 4] += bf16_lo(rr.z); v[8 * qq + 5] += bf16_hi(rr.z);
+                        v[8 * qq + 6] += bf16_lo(rr.w); v[8 * qq + 7] += bf16_hi(rr.w);
+                    }
+                }
+                if (p.relu == 2) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) pk[jj] = interior ? pack_bf16(v[2 * jj], v[2 * jj + 1]) : 0u;  // ZP zero row / column
+                if (p.stat_part) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const float lo = bf16_lo(pk[jj]), hi = bf16_hi(pk[jj]);
+                        st_s += lo + hi;
+                        st_ss = fmaf(lo, lo, fmaf(hi, hi, st_ss));
+                    }
+                }
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(brow + (((uint32_t)qq ^ swz) << 4)), "r"(pk[4 * qq]), "r"(pk[4 * qq + 1]),
+                                 "r"(pk[4 * qq + 2]), "r"(pk[4 * qq + 3])
+                                 : "memory");
+                fence_proxy_async();              // generic-proxy writes -> visible to the TMA store (async proxy)
+                named_bar_sync(1 + grp, 128);     // the whole 128 x 32 chunk is in shared memory
+                if (leader_t) {
+                    tma_store_2d(&tmO, stg + (size_t)j * kCzStgChunk, nb, (int)row0);  // rows >= Q are clipped by TMA
+                    bulk_commit();
+                    if (j > 0) {
+                        bulk_wait_read<1>();      // the previous chunk's store has drained its buffer
+                        setup_slot(j - 1, tile + tile_step);
+                    }
+                }
+            }
+            if (!ok) break;
+            if (leader_t) {
+                bulk_wait_read<0>();
+                setup_slot(c_end - c_begin - 1, tile + tile_step);
+            }
+            if (p.stat_part && row_ok) reinterpret_cast<float2*>(p.stat_part)[(size_t)q * P + n_tile * 2 + grp] = make_float2(st_s, st_ss);
+        }
+        if (leader_t) bulk_wait_all<0>();
     } else {
         // ================= epilogue (warps 3..10) =================
         const int ew = warp - 3;
@@ -397,14 +551,30 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
     p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
     const uint32_t b_stage_bytes = (uint32_t)(p.block_n / (pair ? 2 : 1)) * kBlockK * 2;
-    const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - 512;
+    p.tma_epi = (pair && g_cz_tma && g_cz_dbg == 0 && N % 32 == 0 && p.block_n % 64 == 0 && ((uintptr_t)a->out & 127) == 0 &&
+                 (!a->residual || ((uintptr_t)a->residual & 127) == 0)) ? 1 : 0;
+    const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - 512 - (p.tma_epi ? kCzStgBytes : 0);
     int bst = (int)(budget / b_stage_bytes);
     if (bst > kCzMaxBStages) bst = kCzMaxBStages;
     VPT_CHECK(bst >= 2, "vpt_conv3x3_zp: not enough shared memory for the weight pipeline (W=%d Cout=%d)", W, N);
     p.b_stages = bst;
-    const size_t smem_bytes = 1024 + 2 * (size_t)p.a_stage_bytes + (size_t)bst * b_stage_bytes + (4 + 2 * kCzMaxBStages + 4) * 8 + 16;
+    const size_t smem_bytes = 1024 + 2 * (size_t)p.a_stage_bytes + (size_t)bst * b_stage_bytes + (p.tma_epi ? kCzStgBytes : 0) +
+                              (4 + 2 * kCzMaxBStages + 4 + 8) * 8 + 16;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO, tmR;
+    memset(&tmO, 0, sizeof(tmO));
+    memset(&tmR, 0, sizeof(tmR));
+    if (p.tma_epi) {  // output / residual: [Q][N] bf16, boxes of 128 rows x 32 channels (64-byte rows, SWIZZLE_64B)
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)p.Q};
+        cuuint64_t strides[1] = {(cuuint64_t)N * 2};
+        cuuint32_t box[2] = {32, (cuuint32_t)kBlockM};
+        int r = make_tmap_bf16(&tmO, a->out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (r) return r;
+        if (a->residual) {
+            r = make_tmap_bf16(&tmR, a->residual, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+            if (r) return r;
+        }
+    }
     {
         cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)p.Q};
         cuuint64_t strides[1] = {(cuuint64_t)C * 2};
@@ -437,7 +607,7 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
         long long grid = num_sms();
         if (grid <= 0) grid = 148;
         if (grid > tiles) grid = tiles;
-        conv3x3_zp_kernel<false><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+        conv3x3_zp_kernel<false><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmO, tmR, p);
         VPT_LAUNCH_CHECK();
         return VPT_OK;
     }
@@ -467,12 +637,14 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     long long pairs = max_pairs;
     if (pairs > tiles) pairs = tiles;
     cfg.gridDim = dim3((unsigned)(pairs * 2));
-    VPT_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_zp_kernel<true>, tmA, tmB, p));
+    VPT_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_zp_kernel<true>, tmA, tmB, tmO, tmR, p));
     return VPT_OK;
 }
 
 extern "C" int vpt_set_conv_pair_mode(int32_t on) {
-    vpt::g_cz_dbg = on >> 4;  // bits 4+: epilogue experiment level (tools/conv_bench.py)
+    vpt::g_cz_tma = (on & 0x100) ? 0 : 1;  // bit 8: disable the TMA-store epilogue (A/B knob)
+    on &= 0xff;
+    vpt::g_cz_dbg = on >> 4;  // bits 4..7: epilogue experiment level (tools/conv_bench.py)
     on &= 15;
     vpt::g_cz_pair = on;
     return VPT_OK;

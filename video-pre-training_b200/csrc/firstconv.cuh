@@ -12,6 +12,7 @@
 #pragma once
 #include "attention.cuh"  // ldsm_x4 / mma_bf16_16816
 #include "common.cuh"
+#include "firstconv_tc.cuh"
 
 namespace vpt {
 
@@ -210,7 +211,15 @@ __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uin
 
 }  // namespace vpt
 
-extern "C" int vpt_firstconv_stat_parts(int32_t H, int32_t W) { return (H / 16) * (W / 16); }
+extern "C" int vpt_firstconv_stat_parts(int32_t F, int32_t H, int32_t W, int32_t C0) {
+    if (vpt::firstconv_tc_applies(H, W)) return vpt::firstconv_tc_bands(F, H, (C0 + 127) / 128) * 2 * C0;  // per (band, half, channel)
+    return (H / 16) * (W / 16);
+}
+
+extern "C" int vpt_set_firstconv_mode(int32_t mode) {
+    vpt::g_fc_mode = mode;  // 1: tcgen05 kernel (firstconv_tc.cuh) where it applies; 0: always the mma.sync kernel
+    return VPT_OK;
+}
 
 extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part, int32_t F,
                                   int32_t H, int32_t W, int32_t C0, int32_t zp, void* stream) {
@@ -218,6 +227,22 @@ extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const floa
     VPT_CHECK(img && w && bias && out && F > 0, "vpt_firstconv_pool: null argument");
     VPT_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "vpt_firstconv_pool: H, W must be multiples of 16 (H=%d W=%d)", H, W);
     VPT_CHECK(C0 == 64 || C0 == 128 || C0 == 192 || C0 == 256, "vpt_firstconv_pool: C0=%d not in {64,128,192,256}", C0);
+    if (firstconv_tc_applies(H, W)) {
+        VPT_CHECK(((uintptr_t)img & 15) == 0, "vpt_firstconv_pool: img must be 16-byte aligned");
+        FirstconvTcParams p;
+        memset(&p, 0, sizeof(p));
+        p.img = img; p.w = w; p.bias = bias;
+        p.out = reinterpret_cast<__nv_bfloat16*>(out);
+        p.stat_part = reinterpret_cast<float2*>(stat_part);
+        p.H = H; p.C0 = C0; p.zp = zp ? 1 : 0;
+        p.ncb = (C0 + 127) / 128;
+        p.nbands = firstconv_tc_bands(F, H, p.ncb);
+        p.band_rows = (H / 2) / p.nbands;
+        p.items = (long long)F * p.nbands * p.ncb;
+        if (W == 32) return launch_firstconv_tc<32>(p, stream);
+        if (W == 64) return launch_firstconv_tc<64>(p, stream);
+        return launch_firstconv_tc<128>(p, stream);
+    }
     const long long blocks = (long long)F * (H / 16) * (W / 16);
     VPT_CHECK(blocks < 2147483647LL, "vpt_firstconv_pool: too many tiles");
     const size_t smem = kFcPatchBytes + (size_t)C0 * kFcBPitch * 2 + (size_t)kFcPos * (C0 + 8) * 2;

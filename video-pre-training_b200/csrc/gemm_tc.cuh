@@ -422,7 +422,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 static int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                          const cuuint32_t* box) {
+                          const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -430,7 +430,7 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const cuu
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,

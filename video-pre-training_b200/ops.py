@@ -114,7 +114,7 @@ def firstconv_pool(img, w, bias, C0, zp=True):
     F_, H, W, _ = img.shape
     z = int(zp)
     out = torch.empty((F_, H // 2 + z, W // 2 + z, C0), dtype=BF16, device=img.device)
-    P = nat.lib().vpt_firstconv_stat_parts(H, W)
+    P = nat.lib().vpt_firstconv_stat_parts(F_, H, W, C0)
     part = torch.empty((F_, P, 2), dtype=F32, device=img.device)
     nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, z, _stream()), "vpt_firstconv_pool")
     _count()

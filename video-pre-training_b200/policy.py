@@ -122,6 +122,28 @@ class NetConfig:
             raise NotImplementedError("vpt_b200: first_conv_norm without the conv3d pre-stage is not implemented")
         self.final_hw = (H // 8, W // 8)
 
+    def forward_flops_per_frame(self, head_outputs: int = 121 + 8641 + 1) -> float:
+        """Algorithmic work of one frame through the forward path: 2 x MAC; clipped-causal attention counts
+        `maxlen` keys per query (the band), unmasked attention (IDM) every key of the chunk.  bench.py's roofline uses this."""
+        H, W = self.img_shape[0], self.img_shape[1]
+        fl, cin = 0.0, 3
+        if self.conv3d_out is not None:
+            fl += 2 * H * W * 15 * self.conv3d_out
+            cin = self.conv3d_out
+        for c in self.chans:
+            fl += 2 * H * W * 9 * cin * c
+            H, W = (H + 1) // 2, (W + 1) // 2
+            fl += 4 * 2 * H * W * 9 * c * c
+            cin = c
+        h = self.hidsize
+        fl += 2 * (cin * H * W) * self.cnn_outsize + 2 * self.cnn_outsize * h
+        keys = self.maxlen if self.mask_style == "clipped_causal" else self.maxlen + (self.timesteps or 0)
+        nb = NBASIS if self.mask_style == "clipped_causal" else 0
+        per_layer = 2 * h * h * 4 + 2 * h * nb * self.heads + 2 * 2 * h * h * self.pointwise_ratio
+        per_layer += 4 * keys * h + 2 * nb * keys * self.heads
+        fl += self.n_layers * per_layer + (2 * h * h if self.conv3d_out is None else 0) + 2 * h * head_outputs
+        return fl
+
 
 def _net_schema(cfg: NetConfig) -> "OrderedDict[str, torch.Tensor]":
     """Freshly initialised parameters in the reference's registration order (lib/impala_cnn.py, lib/util.py, lib/xf.py)."""
@@ -770,6 +792,16 @@ class GraphedAct:
                 policy.act({"img": self.img}, self.first, self.state)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graphs = {}
+        self._pin()
+
+    def _weights_fp(self):
+        return _fingerprint(self.policy)
+
+    def _pin(self):
+        """The captured graph holds RAW device pointers into the kernel-layout weight copies: keep those copies alive and remember
+        which parameter versions they were made from (a later load_weights / optimizer step invalidates the graph)."""
+        self._fp = self._weights_fp()
+        self._held = (self.policy.net.prepared(), self.policy._heads_prepared())
 
     def _capture(self, stochastic: bool):
         g = torch.cuda.CUDAGraph()
@@ -796,6 +828,9 @@ class GraphedAct:
                     m_in.copy_(m)
                 k_in.copy_(k)
                 v_in.copy_(v)
+        if self._weights_fp() != self._fp:  # parameters changed since capture: re-layout the weights and re-capture
+            self.graphs = {}
+            self._pin()
         g, ac, res = self.graphs.get(stochastic) or self._capture(stochastic)
         g.replay()
         out = {"log_prob": res["log_prob"], "vpred": res["vpred"]}

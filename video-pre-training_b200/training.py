@@ -58,6 +58,8 @@ class BCTrainer:
         self._wprep = None
         self._wprep_fp = None
         self.debug_grads = None  # set to a dict to capture d loss / d activation under the forward's tap names (tests)
+        self.keep_tape = False   # tests: keep the last forward's tape in `self.last_tape` (tests/forced_replica.py)
+        self.last_tape = None
 
     def _dbg(self, name, g):
         if self.debug_grads is not None:
@@ -187,6 +189,8 @@ class BCTrainer:
             lat_bf16, _, state_out = net._forward_impl(img, first, state_in)
         finally:
             net._tape = None
+        if self.keep_tape:
+            self.last_tape = tape
         pd, _ = pol._heads(lat_bf16, B, t)
         # ---------------- loss + d logits ----------------
         hp = pol._heads_prepared()
