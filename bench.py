@@ -501,6 +501,12 @@ def run_ours(args):
     conv_ms = sum(a.elapsed_time(b) for a, b, _, k, _ in prof if k == "conv")
     conv_fl = sum(f for _, _, f, k, _ in prof if k == "conv")
     pk = peaks()
+    by_shape = {}
+    for a, b, f, k, shp in prof:
+        t, fl_, n = by_shape.get((k, shp), (0.0, 0.0, 0))
+        by_shape[(k, shp)] = (t + a.elapsed_time(b), fl_ + f, n + 1)
+    shape_rows = [{"kind": k, "mnk": list(shp), "launches_per_step": n // args.steps, "ms_per_step": t / args.steps, "tflops": fl_ / t / 1e9}
+                  for (k, shp), (t, fl_, n) in sorted(by_shape.items(), key=lambda kv: -kv[1][0])][:12]
     achieved = g_fl / (g_ms / 1000.0) / 1e12
     flops_frame = pol.net.cfg.forward_flops_per_frame()  # product-side FLOP model (policy.NetConfig), SURVEY 8d
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
@@ -510,7 +516,8 @@ def run_ours(args):
                 "kernel_share_of_step": g_ms / ms if world == 1 else None,
                 "algorithmic_gflop_per_frame": flops_frame / 1e9, "gemm_gflop_per_frame": g_fl / args.steps / frames_per_step / 1e9,
                 "conv_only": {"achieved": conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms else None, "ms_per_step": conv_ms / args.steps},
-                "whole_step_frac_of_flop_roofline": (value / world) * flops_frame / 1e12 / pk["tflops"]}
+                "whole_step_frac_of_flop_roofline": (value / world) * flops_frame / 1e12 / pk["tflops"],
+                "by_shape": shape_rows}
 
     # ---------------- end to end through the public API with HOST buffers ("e2e") ----------------
     state2 = state

@@ -120,6 +120,11 @@ int vpt_set_conv_pair_mode(int32_t on);
  * csrc/conv_zp_t.cuh); 0: the regular orientation.  Changes vpt_conv_zp_stat_parts(128).  Tuning / A-B knob. */
 int vpt_set_conv_swap_mode(int32_t on);
 int vpt_conv_zp_stat_parts(int32_t Cout);
+/* Cout == 128 with the operand-swapped kernel's fragment epilogue (default): its statistics partials are per (tile, warp, frame slot),
+ * not per row.  vpt_conv_zp_t_stat_floats > 0 <=> pass a float buffer of that many elements as stat_part and finalise it with
+ * vpt_conv_zp_t_stats_finalize (mr[f] = mean, rstd over the H*W*128 interior values of frame f). */
+int64_t vpt_conv_zp_t_stat_floats(int32_t F, int32_t H, int32_t W, int32_t Cout);
+int vpt_conv_zp_t_stats_finalize(const float* part, float* mr, int32_t F, int32_t H, int32_t W, float eps, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------------
  * Stack-0 first convolution, fused:  u8 -> /255 -> Conv2d(3->C0, 3x3, pad 1) + bias -> ReLU -> max_pool2d(3, 2, 1)
@@ -128,12 +133,13 @@ int vpt_conv_zp_stat_parts(int32_t Cout);
  *   out  bf16 [F][H/2][W/2][C0] (zp=0) or ZP [F][H/2+1][W/2+1][C0] (zp=1)
  *   stat_part float2 [F][vpt_firstconv_stat_parts(F, H, W, C0)]   (H, W multiples of 16; C0 in {64,128,192,256})
  * Two kernels: for W in {32, 64, 128} with H*W <= 16384 the tcgen05 kernel (csrc/firstconv_tc.cuh: operand-swapped implicit GEMM,
- * thread = channel, 3x3/2 max in registers; its partials are per (row band, column half, CHANNEL): partial index
- * (band*2 + half)*C0 + c, so per-channel sums are available to the caller); otherwise the mma.sync kernel (csrc/firstconv.cuh,
+ * thread = channel, 3x3/2 max in registers; its partials are per (8 pooled rows, column half, CHANNEL): partial index
+ * ((row/8)*2 + half)*C0 + c, so per-channel sums are available to the caller); otherwise the mma.sync kernel (csrc/firstconv.cuh,
  * (H/16)*(W/16) partials per frame).  vpt_set_firstconv_mode(0) forces the mma.sync kernel (A/B knob).
+ * out_f32 != 0 (tcgen05 kernel only): `out` is fp32 in the same layout (precision mode, csrc/precise.cuh).
  * -------------------------------------------------------------------------------------------------------- */
 int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part,
-                       int32_t F, int32_t H, int32_t W, int32_t C0, int32_t zp, void* stream);
+                       int32_t F, int32_t H, int32_t W, int32_t C0, int32_t zp, int32_t out_f32, void* stream);
 int vpt_firstconv_stat_parts(int32_t F, int32_t H, int32_t W, int32_t C0);
 int vpt_set_firstconv_mode(int32_t mode);
 
@@ -142,7 +148,47 @@ int vpt_set_firstconv_mode(int32_t mode);
  *   img u8 [B][T][H][W][3]   w fp32 [C][15] ordered (dt, c), already divided by 255   out bf16 ZP [B*T][H+1][W+1][C]
  *   stat_part float2 [B*T][vpt_conv3d_stat_parts(H, W, C)] */
 int vpt_conv3d_t5(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part, int32_t B, int32_t T,
-                  int32_t H, int32_t W, int32_t C, void* stream);
+                  int32_t H, int32_t W, int32_t C, int32_t out_f32, void* stream);  /* out_f32: fp32 output, same layout (precision mode) */
+
+/* ----------------------------------------------------------------------------------------------------------
+ * On-device action codec (csrc/codec.cuh): table look-ups, one thread per action.
+ *   vpt_codec_to_env    joint policy action -> MineRL env action: lib/action_mapping.py:215-225 (to_factored, camera-meta nulling) +
+ *                       lib/actions.py:154-169 (policy2env; the mu-law camera table cam_lut[nbins] is built by the host with the reference
+ *                       formula, lib/actions.py:96-102).  buttons / camera int64 [n]; lut_btn u8 [njoint][20]; lut_cam_off u8 [njoint];
+ *                       out [n][22] 8-byte words = 20 int64 button flags + 2 float64 camera angles (ONE device-to-host copy per step);
+ *                       *bad counts out-of-range indices.
+ *   vpt_codec_from_env  MineRL env action -> joint policy action: lib/actions.py:171-178 (env2policy; the mu-law quantiser :82-94 as
+ *                       nbins-1 ascending float64 thresholds) + lib/action_mapping.py:193-213 (from_factored, exclusive groups :65-99,
+ *                       inventory override).  buttons int64 [n][20] in lib/actions.py:21-33 order, camera float64 [n][2], strides int64 [9];
+ *                       out int64 [n][3] = (buttons index, camera index, is-null-action flag of agent.py:176-180).
+ * -------------------------------------------------------------------------------------------------------- */
+int vpt_codec_to_env(const int64_t* buttons, const int64_t* camera, const uint8_t* lut_btn, const uint8_t* lut_cam_off, const double* cam_lut,
+                     int32_t nbins, int32_t njoint, int64_t n, int64_t* out, int32_t* bad, void* stream);
+int vpt_codec_from_env(const int64_t* buttons, const double* camera, const double* thresholds, int32_t nbins, const int64_t* strides,
+                       int64_t inventory_idx, int64_t n, int64_t* out, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * fp32-parity precision mode (csrc/precise.cuh; BASELINE north_star "1e-3 rtol fp32", reference arithmetic lib/xf.py:40,55-63).
+ * Contractions stay on vpt_gemm_bf16 (tcgen05): operands split into bf16 hi + lo, three accumulating launches per layer
+ * (hi*hi, lo*hi, hi*lo; fp32 output used as the fp32 residual of the next launch).  These entry points are the fp32 glue between
+ * them.  All tensors fp32 row-major [rows][C] unless noted.
+ *   vpt_group_stats_f32   mr[g] = (mean, rstd) over `per_group` consecutive elements (GroupNorm(1) per frame / LayerNorm per row)
+ *   vpt_norm_split_f32    u = [(x - mean_g) * rstd_g] * gamma[c] + beta[c] (mr / gamma / beta optional; group = i / per_group);
+ *                         hi = bf16(u), lo = bf16(u - hi) (both or neither) and / or out_f32 = u
+ *   vpt_add_f32           out = a + b (b optional), optional ReLU
+ *   vpt_maxpool3s2_f32    max_pool2d(3, 2, 1) on NHWC fp32 [F][H][W][C] -> [F][H/2][W/2][C] (lib/impala_cnn.py:117)
+ *   vpt_attention_f32     lib/xf.py:18-71 with the mask of lib/masked_attention.py:11-94 and the relative term of lib/xf.py:265-271:
+ *                         q [B*t][h], full_k / full_v [B][maxlen+t][h], R [B*t][10*heads] or NULL, b_nd [10][maxlen], first u8 [B][t],
+ *                         state_mask u8 [B][maxlen] or NULL (= all False), out [B*t][h]; head_dim 128; causal = clipped_causal mask
+ * -------------------------------------------------------------------------------------------------------- */
+int vpt_group_stats_f32(const float* x, float* mr, int64_t groups, int64_t per_group, float eps, void* stream);
+int vpt_norm_split_f32(const float* x, const float* mr, const float* gamma, const float* beta, void* hi, void* lo, float* out_f32,
+                       int64_t n, int32_t C, int64_t per_group, void* stream);
+int vpt_add_f32(const float* a, const float* b, float* out, int64_t n, int32_t relu, void* stream);
+int vpt_maxpool3s2_f32(const float* in, float* out, int64_t F, int32_t H, int32_t W, int32_t C, void* stream);
+int vpt_attention_f32(const float* q, const float* full_k, const float* full_v, const float* R, const float* b_nd, const uint8_t* first,
+                      const uint8_t* state_mask, float* out, int32_t B, int32_t t, int32_t maxlen, int32_t heads, int32_t causal,
+                      void* stream);
 int vpt_conv3d_stat_parts(int32_t H, int32_t W, int32_t C);
 
 /* max_pool2d(kernel 3, stride 2, pad 1) on a non-negative NHWC bf16 tensor (lib/impala_cnn.py:117).

@@ -56,7 +56,7 @@ def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, 
     if relu == 1:
         v = v.relu()
     if residual is not None:
-        v = v + residual.reshape(M, N).float()
+        v = v + residual.reshape(M, -1)[:, :N].float()
     if relu == 2:
         v = v.relu()
     v = v * out_scale
@@ -126,22 +126,78 @@ def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None,
     return res, (_frame_stats(o) if want_stats else None)
 
 
-def firstconv_pool(img, w, bias, C0, zp=True):
+def firstconv_pool(img, w, bias, C0, zp=True, out_f32=False):
     F_, H, W, _ = img.shape
     x = img.float().permute(0, 3, 1, 2)
     wt = w.reshape(C0, 3, 3, 3).permute(0, 3, 1, 2)  # [C0][ky][kx][c] -> OIHW
     y = F.relu(F.conv2d(x, wt, bias, padding=1))
-    y = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)
+    y = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(F32 if out_f32 else BF16)
     return (to_zp(y) if zp else y), _frame_stats(y)
 
 
-def conv3d_t5(img, w, bias, C):
+def conv3d_t5(img, w, bias, C, out_f32=False):
     B, T, H, W, _ = img.shape
     x = img.float().permute(0, 4, 1, 2, 3)                       # b c t h w
     wt = w.reshape(C, 5, 3).permute(0, 2, 1).reshape(C, 3, 5, 1, 1)  # [C][dt][c] -> [C][c][dt][1][1]
     y = F.relu(F.conv3d(x, wt, bias, padding=(2, 0, 0)))         # per-sample zero padding in time == batched conv3d
-    y = y.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, C).contiguous().to(BF16)
+    y = y.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, C).contiguous().to(F32 if out_f32 else BF16)
     return to_zp(y), _frame_stats(y)
+
+
+# ---- fp32-parity precision mode (csrc/precise.cuh) ----
+def group_stats_f32(x, groups, eps=1e-5):
+    v = x.reshape(groups, -1).double()
+    mean = v.mean(1)
+    var = ((v * v).mean(1) - mean * mean).clamp(min=0)
+    return torch.stack([mean, 1.0 / torch.sqrt(var + eps)], 1).float()
+
+
+def norm_split_f32(x, mr=None, gamma=None, beta=None, groups=1, split=True, want_f32=False):
+    u = x
+    if mr is not None:
+        v = x.reshape(groups, -1)
+        u = ((v - mr[:, 0:1]) * mr[:, 1:2]).reshape(x.shape)
+    if gamma is not None:
+        u = u * gamma
+    if beta is not None:
+        u = u + beta
+    hi = u.to(BF16) if split else None
+    lo = (u - hi.float()).to(BF16) if split else None
+    return hi, lo, (u.clone() if want_f32 else None)
+
+
+def add_f32(a, b=None, relu=False, out=None):
+    v = a if b is None else a + b
+    return v.relu() if relu else v.clone()
+
+
+def maxpool3s2_f32(x):
+    return F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+
+
+def attention_f32(q, full_k, full_v, R, b_nd, first_u8, smask_u8, B, t, maxlen, heads, causal=True):
+    smask = smask_u8
+    h = q.shape[-1]
+    D = h // heads
+    T = maxlen + t
+    qq = q.reshape(B, t, heads, D).permute(0, 2, 1, 3)
+    k = full_k.reshape(B, T, heads, D).permute(0, 2, 1, 3)
+    v = full_v.reshape(B, T, heads, D).permute(0, 2, 1, 3)
+    logit = qq @ k.transpose(-1, -2) / D
+    if causal:
+        i = torch.arange(t)[:, None]
+        j = torch.arange(T)[None, :]
+        d = maxlen + i - j
+        band = (d >= 0) & (d < maxlen)
+        memok = torch.zeros(B, maxlen, dtype=torch.bool) if smask is None else (smask.reshape(B, maxlen) != 0)
+        memok = memok & (first_u8[:, 0] == 0)[:, None]
+        colok = torch.cat([memok, torch.ones(B, t, dtype=torch.bool)], 1)
+        allowed = band[None] & colok[:, None, :]
+        E = R.reshape(B, t, heads, -1).permute(0, 2, 1, 3) @ b_nd
+        extra = torch.gather(E, 3, d.clamp(0, maxlen - 1)[None, None].expand(B, heads, t, T)) * band[None, None]
+        logit = logit + extra + (~allowed[:, None]).float() * -1e9
+    w = torch.softmax(logit, -1)
+    return (w @ v).permute(0, 2, 1, 3).reshape(B * t, h)
 
 
 def maxpool3s2(x, zp=True):
@@ -381,3 +437,40 @@ def softmax_bwd(logp, idx, scale, out, col0):
     g[torch.arange(g.shape[0]), idx.reshape(-1).long()] -= 1.0
     out[:, col0:col0 + n] = (g * scale).to(out.dtype)
     return out
+
+
+# ---- on-device action codec (csrc/codec.cuh) ----
+def codec_to_env(buttons, camera, lut_btn, lut_cam_off, cam_lut, nbins):
+    b, c = buttons.reshape(-1).long(), camera.reshape(-1).long()
+    cy, cx = c // nbins, c % nbins
+    off = lut_cam_off[b] != 0
+    cy = torch.where(off, torch.full_like(cy, nbins // 2), cy)
+    cx = torch.where(off, torch.full_like(cx, nbins // 2), cx)
+    out = torch.empty((b.numel(), 22), dtype=torch.int64)
+    out[:, :20] = lut_btn.reshape(-1, 20)[b].long()
+    out[:, 20] = cam_lut[cy].view(torch.int64)
+    out[:, 21] = cam_lut[cx].view(torch.int64)
+    return out, torch.zeros(1, dtype=torch.int32)
+
+
+def codec_from_env(buttons, camera, thresholds, nbins, strides, inventory_idx):
+    on = buttons != 0
+    n = buttons.shape[0]
+    hot = torch.zeros(n, dtype=torch.int64)
+    for k in range(9):
+        hot = torch.where(on[:, 11 + k], torch.full_like(hot, k + 1), hot)
+
+    def pair(a, b, cancel):
+        r = torch.where(on[:, b], 2, torch.where(on[:, a], 1, 0))
+        return torch.where(on[:, a] & on[:, b], 0, r) if cancel else r
+
+    binv = (camera[:, :, None] >= thresholds[None, None, :]).sum(-1)
+    null = nbins // 2
+    cam_null = (binv == null).all(1)
+    parts = [hot, pair(2, 1, True), pair(4, 5, True), pair(7, 6, False), on[:, 8].long(), on[:, 9].long(), on[:, 0].long(), on[:, 3].long(), (~cam_null).long()]
+    joint = sum(p_ * s_ for p_, s_ in zip(parts, strides.tolist()))
+    cidx = binv[:, 0] * nbins + binv[:, 1]
+    inv = buttons[:, 10] == 1
+    joint = torch.where(inv, torch.full_like(joint, inventory_idx), joint)
+    cidx = torch.where(inv, torch.full_like(cidx, null * nbins + null), cidx)
+    return torch.stack([joint, cidx, ((~on.any(1)) & cam_null).long()], 1)

@@ -181,3 +181,56 @@ def test_ingest_kernels_bit_exact():
     for f in range(F_):
         exp = resize_oracle.ingest(frames[f], (128, 128), cur, alpha, xy[f])
         assert np.array_equal(got[f], exp), f
+
+
+def _codec_cases(c, n=50000, seed=0):
+    """Every joint action (x3 random cameras) for to_env; random env actions + camera angles exactly at / next to every quantiser
+    threshold, null actions and inventory presses for from_env."""
+    g = torch.Generator().manual_seed(seed)
+    b = torch.arange(8641).repeat_interleave(3)[:, None]
+    cam = torch.randint(0, 121, (b.shape[0], 1), generator=g)
+    rng = np.random.default_rng(seed)
+    btn = (rng.random((n, 20)) < 0.15).astype(np.int64)
+    btn[:500] = 0
+    camv = rng.uniform(-12, 12, (n, 2))
+    camv[:250] = 0.0
+    thr = c._device_tables("cpu")["thr"].numpy()
+    k = len(thr)
+    camv[1000:1000 + k, 0] = thr
+    camv[2000:2000 + k, 0] = np.nextafter(thr, -np.inf)
+    camv[3000:3000 + k, 1] = np.nextafter(thr, np.inf)
+    return b, cam, btn, camv
+
+
+def _check_codec(c, dev):
+    b, cam, btn, camv = _codec_cases(c)
+    got = c.to_env_device({"buttons": b.to(dev), "camera": cam.to(dev)}) if dev != "cpu" else None
+    ref = c.policy2env(c.to_factored({"buttons": b.numpy(), "camera": cam.numpy()}))
+    if got is None:  # CPU: through the emulated op (the wrapper's .cpu() path is the same)
+        got = c.to_env_device({"buttons": b, "camera": cam})
+    for name in A.BUTTONS:
+        assert got[name].dtype == np.int64 and np.array_equal(got[name], ref[name]), name
+    assert got["camera"].dtype == np.float64 and np.array_equal(got["camera"], ref["camera"])  # bit-exact float64 angles
+    env = {name: btn[:, i] for i, name in enumerate(A.BUTTONS)}
+    env["camera"] = camv
+    a = c.env2policy(env)
+    ref2 = c.from_factored(a)
+    null_ref = (a["buttons"] == 0).all(1) & (a["camera"] == c.null_bin).all(1)
+    ac, is_null = c.from_env_device(torch.from_numpy(btn).to(dev), torch.from_numpy(camv).to(dev))
+    assert np.array_equal(ac["buttons"].cpu().numpy(), ref2["buttons"]) and np.array_equal(ac["camera"].cpu().numpy(), ref2["camera"])
+    assert np.array_equal(is_null.cpu().numpy(), null_ref) and null_ref.sum() >= 250
+
+
+def test_device_codec_tables_match_the_host_codec():
+    """SURVEY f-3: the tables / thresholds the on-device codec uses, checked through the test-only emulation of the two kernels against
+    the numpy codec (which test_codec_matches_live_reference pins to the reference)."""
+    from common import emulation
+    with emulation():
+        _check_codec(A.ActionCodec(**A.ACTION_TRANSFORMER_KWARGS), "cpu")
+
+
+@pytest.mark.gpu
+def test_device_codec_kernels_bit_exact():
+    """vpt_codec_to_env / vpt_codec_from_env on the GPU == the numpy codec on every joint action and on 50k env actions incl. camera
+    angles at the quantiser thresholds (integer + float64 bit patterns, so: exact)."""
+    _check_codec(A.ActionCodec(**A.ACTION_TRANSFORMER_KWARGS), "cuda")

@@ -117,3 +117,15 @@ def test_emulation_mirrors_the_ops_api():
             mismatched.append((name, list(inspect.signature(fn).parameters), list(inspect.signature(emu).parameters)))
     assert not missing, f"ops without an emulation: {missing}"
     assert not mismatched, mismatched
+
+
+def test_precise_mode_host_logic_matches_oracle(emulated):
+    """fp32-parity mode (precise.py): launch order, hi/lo weight splits, explicit norms, KV bookkeeping -- through the emulated ops."""
+    pol, sd, cfg = make_policy(small_kwargs())
+    pol.set_precision("fp32")
+    for o in run_chunks(pol, sd, cfg, 2, [8, 8, 5], "cpu", first_at=(1, 1)):
+        for k in o["pd_o"]:
+            assert rel_err(o["pd"][k], o["pd_o"][k]) < 1e-4, k
+        assert (o["v"] - o["v_o"]).abs().max() < 1e-3
+        for (m, (kk, vv)), (m_o, (k_o, v_o)) in zip(o["st"], o["st_o"]):
+            assert torch.equal(m, m_o) and torch.allclose(kk, k_o, rtol=1e-3, atol=1e-4) and torch.allclose(vv, v_o, rtol=1e-3, atol=1e-4)

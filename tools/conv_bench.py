@@ -9,7 +9,7 @@ l = nat.lib()
 g = torch.Generator().manual_seed(0)
 shapes = [(64, 128, 256, 2048, False), (32, 256, 256, 2048, False), (32, 256, 256, 2048, True), (16, 256, 256, 2048, True),
           (64, 128, 128, 2048, True)]
-variants = [("tma-epilogue", 1), ("r1-epilogue", 0x101)]
+variants = [("tma/frag-epi", 1, 1), ("r1-epilogue", 0x101, 3)]
 for (HW, Cin, N, F_, res) in shapes:
     x = torch.zeros(F_, HW + 1, HW + 1, Cin, dtype=torch.bfloat16, device="cuda")
     x[:, :HW, :HW] = torch.randn(F_, HW, HW, Cin, device="cuda").to(torch.bfloat16)
@@ -22,8 +22,9 @@ for (HW, Cin, N, F_, res) in shapes:
     S1 = torch.randn(9, N, device="cuda"); S2 = torch.randn(9, N, device="cuda")
     fl = 2.0 * F_ * HW * HW * N * 9 * Cin
     ref = None
-    for (name, mode) in variants:
+    for (name, mode, swap) in variants:
         l.vpt_set_conv_pair_mode(mode)
+        l.vpt_set_conv_swap_mode(swap)
         for _ in range(2):
             out, st = ops.conv3x3_zp(x, Wb, HW, HW, mr=mr, S1=S1, S2=S2, relu=1, residual=r, want_stats=True)
         torch.cuda.synchronize()
@@ -38,4 +39,4 @@ for (HW, Cin, N, F_, res) in shapes:
         err = (out.float() - ref[0]).abs().max().item()
         serr = (st - ref[1]).abs().max().item()
         print(f"HW={HW} Cin={Cin} N={N} F={F_} res={int(res)}: {name:13s}: {ms:7.3f} ms  {fl/ms/1e9:7.0f} TFLOP/s (algorithmic)  max diff vs first {err:.1e} stats {serr:.1e}", flush=True)
-l.vpt_set_conv_pair_mode(1)
+l.vpt_set_conv_pair_mode(1); l.vpt_set_conv_swap_mode(1)

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libvpt_b200.so")
 SRC = os.path.join(_HERE, "csrc", "vpt_b200.cu")
 HEADER = os.path.join(_ROOT, "include", "vpt_b200.h")
 
+ABI_VERSION = 2  # == VPT_ABI_VERSION in include/vpt_b200.h (checked against the loaded library)
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -77,13 +79,22 @@ SIGNATURES = {
     "vpt_set_default_cluster": (_I, [_I]),
     "vpt_conv3x3_zp": (_I, [C.POINTER(ConvZpArgs), _P]),
     "vpt_conv_zp_stat_parts": (_I, [_I]),
+    "vpt_conv_zp_t_stat_floats": (_L, [_I, _I, _I, _I]),
+    "vpt_conv_zp_t_stats_finalize": (_I, [_P, _P, _I, _I, _I, _F, _P]),
     "vpt_set_conv_pair_mode": (_I, [_I]),
     "vpt_set_conv_swap_mode": (_I, [_I]),
     "vpt_debug_set": (_I, [_I, _I]),
-    "vpt_firstconv_pool": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vpt_firstconv_pool": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vpt_firstconv_stat_parts": (_I, [_I, _I, _I, _I]),
     "vpt_set_firstconv_mode": (_I, [_I]),
-    "vpt_conv3d_t5": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vpt_conv3d_t5": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "vpt_group_stats_f32": (_I, [_P, _P, _L, _L, _F, _P]),
+    "vpt_norm_split_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _L, _P]),
+    "vpt_add_f32": (_I, [_P, _P, _P, _L, _I, _P]),
+    "vpt_maxpool3s2_f32": (_I, [_P, _P, _L, _I, _I, _I, _P]),
+    "vpt_attention_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vpt_codec_to_env": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P, _P, _P]),
+    "vpt_codec_from_env": (_I, [_P, _P, _P, _I, _P, _L, _L, _P, _P]),
     "vpt_conv3d_stat_parts": (_I, [_I, _I, _I]),
     "vpt_maxpool3s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vpt_pool_stat_parts": (_I, [_I, _I, _I]),
@@ -138,8 +149,8 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)  # AttributeError if the ABI is out of sync with the header
             fn.restype, fn.argtypes = res, args
-        if l.vpt_abi_version() != 1:
-            raise NativeError("libvpt_b200.so ABI version mismatch")
+        if l.vpt_abi_version() != ABI_VERSION:
+            raise NativeError(f"libvpt_b200.so ABI version {l.vpt_abi_version()} != {ABI_VERSION} (rebuild: __graft_entry__.build())")
         _lib = l
     return _lib
 

@@ -110,6 +110,57 @@ class ActionCodec:
             xy = np.sign(xy) * (1.0 / self.mu) * ((1.0 + self.mu) ** np.abs(xy) - 1.0) * self.maxval
         return xy
 
+    # ---- on-device versions (csrc/codec.cuh): tables built here with the formulas above, look-ups on the GPU -------------------
+    def _device_tables(self, device):
+        device = torch.device(device)
+        t = getattr(self, "_dev_tables", None)
+        if t is None or t["device"] != device:
+            bins = np.arange(self.n_bins)
+            cam_lut = self.undiscretize_camera(bins).astype(np.float64)            # lib/actions.py:96-102, one entry per bin
+            # bin thresholds of discretize_camera: thr[k] = the smallest float64 x with discretize(x) >= k + 1, found by bisection on the
+            # host formula itself (monotone), so the device binning `#{k: x >= thr[k]}` reproduces numpy's log / round bit for bit
+            thr = np.empty(self.n_bins - 1, dtype=np.float64)
+            for k in range(self.n_bins - 1):
+                lo, hi = -float(self.maxval), float(self.maxval)
+                assert self.discretize_camera(np.array(lo)) <= k < self.discretize_camera(np.array(hi))
+                while True:
+                    mid = lo + (hi - lo) / 2
+                    if mid == lo or mid == hi:
+                        break
+                    if self.discretize_camera(np.array(mid)) >= k + 1:
+                        hi = mid
+                    else:
+                        lo = mid
+                thr[k] = hi
+            t = dict(device=device, lut_btn=torch.from_numpy(self.idx_to_factored.astype(np.uint8)).contiguous().to(device),
+                     lut_cam_off=torch.from_numpy(self.idx_camera_off.astype(np.uint8)).to(device), cam_lut=torch.from_numpy(cam_lut).to(device),
+                     thr=torch.from_numpy(thr).to(device), strides=torch.from_numpy(self.strides.astype(np.int64)).to(device))
+            self._dev_tables = t
+        return t
+
+    def to_env_device(self, ac):
+        """{"buttons": int64 (..., 1), "camera": int64 (..., 1)} device tensors (what `act` returns) -> MineRL env action dict of numpy
+        arrays, == policy2env(to_factored(ac)): the look-ups run on the GPU (`vpt_codec_to_env`) and ONE (n, 22)-word tensor crosses
+        to the host instead of two index tensors followed by numpy table gathers."""
+        from . import ops
+        b, c = ac["buttons"], ac["camera"]
+        t = self._device_tables(b.device)
+        lead = tuple(b.shape[:-1])
+        words, bad = ops.codec_to_env(b.reshape(-1).contiguous(), c.reshape(-1).contiguous(), t["lut_btn"], t["lut_cam_off"], t["cam_lut"], self.n_bins)
+        host = words.cpu().numpy()
+        out = {name: host[:, i].reshape(lead) for i, name in enumerate(BUTTONS)}
+        out["camera"] = host[:, 20:22].view(np.float64).reshape(*lead, 2)
+        return out
+
+    def from_env_device(self, buttons, camera):
+        """MineRL env actions on the device -- buttons int64 (n, 20) in `BUTTONS` order, camera float64 (n, 2) degrees -> (joint action
+        dict of int64 (n, 1) device tensors, is-null bool (n,)) == from_factored(env2policy(.)) + the null-action test of agent.py:176-180."""
+        from . import ops
+        t = self._device_tables(buttons.device)
+        out = ops.codec_from_env(buttons.to(torch.int64).contiguous(), camera.to(torch.float64).contiguous(), t["thr"], self.n_bins, t["strides"],
+                                 self.inventory_idx)
+        return dict(buttons=out[:, 0:1], camera=out[:, 1:2]), out[:, 2] != 0
+
     def policy2env(self, factored):
         """lib/actions.py:154-169."""
         out = {name: factored["buttons"][..., i] for i, name in enumerate(BUTTONS)}
@@ -236,7 +287,9 @@ class MineRLAgent:
         return {"img": resize_frames(pov[None], AGENT_RESOLUTION)}
 
     def _agent_action_to_env(self, agent_action):
-        """agent.py:151-164."""
+        """agent.py:151-164.  Device tensors (what `act` returns) are decoded on the GPU: one small device-to-host copy per step."""
+        if all(isinstance(v, torch.Tensor) and v.is_cuda for v in agent_action.values()):
+            return self.codec.to_env_device(agent_action)
         action = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in agent_action.items()}
         return self.codec.policy2env(self.codec.to_factored(action))
 
@@ -282,7 +335,6 @@ class IDMAgent:
         """inverse_dynamics_model.py:45-48."""
         from .checkpoint import load_weights
         load_weights(self.policy, path, map_location=self.device)
-        self._step = None  # a captured rollout graph belongs to the old weights (GraphedAct re-checks too)
         self.reset()
 
     def reset(self):

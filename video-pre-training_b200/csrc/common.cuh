@@ -87,19 +87,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the time limit passes, instead of
+// burning issue slots in a spin loop (round-2 ncu of the first-conv kernel: ~45 % of all executed instructions were BRA / SYNCS / BSSY
+// of waiting warps, competing with the 12 working warps of the SM).
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // Waits for the phase with the given parity to complete.  A watchdog (~2 s of polling) turns a protocol bug
 // into a recorded error + early exit rather than a hung GPU.
+// The shared error flag lives in global memory: polling it on EVERY failed try_wait made every short wait cost at least one L2 round
+// trip on an address that all waiting warps of all SMs hammer at once -- invisible next to the ~15 us tiles of the conv kernels, but
+// it was most of the time of the first-conv kernel, whose tiles last ~0.5 us (round-2 measurement).  try_wait itself blocks for a
+// hardware-defined interval, so the flag is now looked at once per 64 failed attempts.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned int code) {
     if (mbar_try_wait(bar, parity)) return true;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (*(volatile unsigned int*)&g_device_error != 0u) return false;
-        if (clock64() - t0 > 3000000000LL) {
-            atomicCAS(&g_device_error, 0u, code);
-            return false;
+    const long long t0 = clock64();
+    for (unsigned int it = 1;; ++it) {
+        if (mbar_try_wait_sleep(bar, parity, 20000u)) return true;
+        if ((it & 63u) == 0u) {
+            if (*(volatile unsigned int*)&g_device_error != 0u) return false;
+            if (clock64() - t0 > 3000000000LL) {
+                atomicCAS(&g_device_error, 0u, code);
+                return false;
+            }
         }
     }
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -651,7 +651,7 @@ extern "C" int vpt_set_conv_pair_mode(int32_t on) {
 }
 
 extern "C" int vpt_conv_zp_stat_parts(int32_t Cout) {
-    if (Cout == 128 && vpt::g_cz_swap_enabled()) return 1;  // swapped kernel: complete row sums
+    if (Cout == 128 && vpt::g_cz_swap_enabled()) return 1;  // swapped kernel, round-1 epilogue: complete row sums (see vpt_conv_zp_t_stat_floats)
     int bn, nt;
     vpt::choose_block_n(Cout, &bn, &nt);
     return nt * 2;

@@ -30,8 +30,23 @@ struct ConvZpTParams {
     int dbg_skip_epilogue;
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
-    float* stat_part;  // [Q] float2 (complete row sums) or null
+    float* stat_part;  // epi_mode 0: [Q] float2 (complete row sums) or null; epi_mode 1: [num_tiles][8 warps][2 frame slots] float2
+    int epi_mode;      // 1: fragment epilogue (tcgen05.ld.16x256b -> stmatrix.trans -> TMA store, TMA-prefetched residual); 0: round-1 epilogue
+    int stage_off;     // epi_mode 1: byte offset of the 64 KB output / residual staging area (after the weight stages)
 };
+
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void stsm_x4_trans(uint32_t addr, const uint32_t (&r)[4]) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 
 // lane L ends up with the sum over the warp's 32 lanes of x[L]  (31 shuffles)
 __device__ __forceinline__ float transpose_reduce32(float (&x)[32], int lane) {
@@ -49,22 +64,26 @@ __device__ __forceinline__ float transpose_reduce32(float (&x)[32], int lane) {
 }
 
 __global__ void __launch_bounds__(kCzThreads, 1)
-conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvZpTParams p) {
+conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+                    const __grid_constant__ CUtensorMap tmR, const ConvZpTParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     constexpr uint32_t w_stage_bytes = 128 * kBlockK * 2;  // [128 channels][64 k]
     uint8_t* smem_x = smem;                                 // 2 activation-span stages
     uint8_t* smem_w = smem + 2 * (size_t)p.a_stage_bytes;   // weight tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + (size_t)p.b_stages * w_stage_bytes);
+    uint8_t* smem_stage = smem + p.stage_off;               // epi_mode 1: 4 boxes [128 pixels][64 channels] bf16, SWIZZLE_128B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + (size_t)p.b_stages * w_stage_bytes + (p.epi_mode == 1 ? 65536 : 0));
     uint64_t* x_full = bars;
     uint64_t* x_empty = bars + 2;
     uint64_t* w_full = bars + 4;
     uint64_t* w_empty = bars + 4 + kCzMaxBStages;
     uint64_t* tmem_full_bar = bars + 4 + 2 * kCzMaxBStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    float* s_tile0 = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // 2 x [64 pixels][132] fp32: transposed quarter tiles
+    uint64_t* slot_ready = tmem_empty_bar + 2;  // epi_mode 1: [4 boxes] staging box free (and its residual tile landed)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(slot_ready + 4);
+    float* s_tile0 = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // 2 x [64 pixels][132] fp32: transposed quarter tiles (epi_mode 0)
+    float4* s_info2 = reinterpret_cast<float4*>(tmem_ptr_smem + 4);  // epi_mode 1: [2 buffers][2 halves][128 pixels] (ga, gb, cls, frame slot)
     float4* s_info0 = reinterpret_cast<float4*>(s_tile0 + 2 * 64 * kCtPitch);  // 2 x [64]: per-row (ga, gb, cls)
 
     const int warp = threadIdx.x >> 5;
@@ -73,6 +92,11 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
+        if (p.epi_mode == 1) {
+            tma_prefetch_desc(&tmO);
+            if (p.residual) tma_prefetch_desc(&tmR);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(&slot_ready[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&x_full[i], 1);
             mbar_init(&x_empty[i], 1);
@@ -166,6 +190,165 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (ok) umma_commit(&tmem_full_bar[as]);
             }
         }
+    } else if (p.epi_mode == 1) {
+        // ================= epilogue v2 (warps 3..10): fragments -> stmatrix.trans -> TMA store =================
+        // Round-1 ncu on this kernel: tensor pipe 55-64 % active with the L1/shared pipe at 47 % -- the fp32 transposing store + the
+        // row-major second pass cost ~3000 shared/L1 wavefronts per tile on the pipe the UMMA operand fetch needs.  Here the
+        // accumulator is read with tcgen05.ld.16x256b, whose register layout is the mma.sync accumulator fragment (thread T: lanes
+        // T/4 and T/4+8 = channels, columns 2(T%4), +1 = pixels), folded / ReLU'd / rounded in that layout, and four 8x8 bf16 blocks
+        // at a time are written TRANSPOSED by stmatrix into a [pixel][channel] SWIZZLE_128B staging box that one thread hands to TMA
+        // (UTMASTG).  The residual tile of the next tile is TMA-prefetched into the same box and read with ldmatrix.trans (same
+        // fragment layout); the output overwrites it in place.  ~16 stmatrix + 16 ldmatrix per warp and tile instead of ~380 accesses.
+        // Statistics: per-thread sums split by the (at most two) frames a 256-pixel tile touches, one float2 pair per warp and tile.
+        const int ew = warp - 3;
+        const int quarter = warp & 3;        // TMEM lane quarter = channels [32 quarter, +32)
+        const int g = ew >> 2;               // pixel half of the tile: columns [128 g, +128)
+        const int box = (quarter >> 1) * 2 + g;  // staging box: channels [64 (quarter/2), +64) x this half's 128 pixels
+        uint8_t* stg = smem_stage + (size_t)box * 16384;
+        const uint32_t stg_u32 = smem_u32(stg);
+        uint64_t* slot = &slot_ready[box];
+        const bool leader_t = ((quarter & 1) == 0) && lane == 0;
+        const int T4 = lane >> 2, tq = lane & 3;
+        // fold tables of the interior border class (cls 4) for this thread's four channels c(hh, u) = 32 quarter + 16 hh + 8 u + T4
+        float s1c[4], s2c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quarter * 32 + (i >> 1) * 16 + (i & 1) * 8 + T4;
+            s1c[i] = p.S1 ? __ldg(p.S1 + 4 * 128 + c) : 0.f;
+            s2c[i] = p.S2 ? __ldg(p.S2 + 4 * 128 + c) : 0.f;
+        }
+        auto setup_slot = [&](long long tile) {  // box leader: the box is free -> arm it for `tile`
+            if (tile >= p.num_tiles) return;
+            if (p.residual) {
+                mbar_expect_tx(slot, 16384u);
+                tma_load_2d(stg, &tmR, slot, (quarter >> 1) * 64, (int)(tile * kCtPix + 128 * g));
+            } else {
+                mbar_arrive(slot);
+            }
+        };
+        if (leader_t) setup_slot(blockIdx.x);
+        // ldmatrix / stmatrix row address of this lane inside a 16-pixel block: matrix m = lane / 8 <-> (u = m & 1: channels +8, pxo = m / 2:
+        // pixels +8), row = lane % 8; 16-byte chunk = (quarter & 1) * 4 + hh * 2 + u of the 128-byte row, XOR-swizzled with the row index
+        const int m_u = (lane >> 3) & 1, m_pxo = lane >> 4, m_row = lane & 7;
+        int local = 0;
+        bool ok = true;
+        for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
+            const long long q0 = tile * kCtPix + 128 * g;
+            const unsigned fA = (unsigned)((tile * kCtPix) / p.FS);  // first frame this tile touches (the other one, if any, is fA + 1)
+            float4* s_info = s_info2 + ((local & 1) * 2 + g) * 128;
+            {   // per-pixel constants of this half: thread (quarter, lane) fills pixel 32 quarter + lane
+                const long long q = q0 + quarter * 32 + lane;
+                float4 info = make_float4(1.f, 0.f, -2.f, 0.f);
+                if (q < p.Q) {
+                    const unsigned qq = (unsigned)q, f = qq / (unsigned)p.FS, r = qq - f * (unsigned)p.FS;
+                    const int y = (int)(r / (unsigned)p.Wp), x = (int)r - y * p.Wp;
+                    info.w = (float)(f - fA);
+                    if (y < p.H && x < p.W) {
+                        const int cy = (y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1);
+                        const int cx = (x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1);
+                        float ga = 1.f, gb = 0.f;
+                        if (p.mr) {
+                            const float mean = __ldg(p.mr + 2 * f), rstd = __ldg(p.mr + 2 * f + 1);
+                            ga = rstd;
+                            gb = rstd * mean;
+                        }
+                        info = make_float4(ga, gb, (float)(cy * 3 + cx), info.w);
+                    } else {
+                        info.z = -1.f;
+                    }
+                }
+                s_info[quarter * 32 + lane] = info;
+            }
+            named_bar_sync(5 + g, 128);  // the half's info table is complete (double buffered: no second barrier needed)
+            float sA = 0.f, ssA = 0.f, sB = 0.f, ssB = 0.f;
+            if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x810u))) break;
+            tc_fence_after();
+            if (!mbar_wait(slot, (uint32_t)local & 1u, 0x820u)) asm volatile("trap;");  // (a break would desynchronise the named barriers)
+            for (int pb = 0; pb < 8; ++pb) {  // 16-pixel blocks
+                uint32_t acc[2][8];
+                const uint32_t tcol = (uint32_t)(as * kAccStageCols + 128 * g + 16 * pb);
+                tmem_ld_16x256b_x2(tmem_base + ((uint32_t)(quarter * 32) << 16) + tcol, acc[0]);
+                tmem_ld_16x256b_x2(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + tcol, acc[1]);
+                tmem_ld_wait();
+                if (pb == 7) {  // accumulator stage fully read
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                }
+                // this lane's ldmatrix / stmatrix row: pixel 16 pb + 8 m_pxo + m_row of the half
+                const int mpx = 16 * pb + 8 * m_pxo + m_row;
+                const uint32_t row_addr = stg_u32 + (uint32_t)mpx * 128u;
+                float4 inf[4];  // pixels 16 pb + 8 pxo + 2 tq + e, index pxo * 2 + e
+#pragma unroll
+                for (int i = 0; i < 4; ++i) inf[i] = s_info[16 * pb + 8 * (i >> 1) + 2 * tq + (i & 1)];
+                float ps[4] = {0.f, 0.f, 0.f, 0.f}, pss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t chunk = (uint32_t)((quarter & 1) * 4 + hh * 2 + m_u);
+                    const uint32_t maddr = row_addr + ((chunk ^ (uint32_t)(mpx & 7)) << 4);
+                    uint32_t res[4] = {0u, 0u, 0u, 0u};
+                    if (p.residual) ldsm_x4_trans(maddr, res);
+                    uint32_t outp[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {  // matrix m: u = m & 1 (channel +8), pxo = m >> 1 (pixel +8)
+                        const int u = m & 1, pxo = m >> 1;
+                        float v[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float4 in = inf[pxo * 2 + e];
+                            const int cls = (int)in.z;
+                            float a1 = s1c[hh * 2 + u], a2 = s2c[hh * 2 + u];
+                            if (cls != 4 && cls >= 0) {
+                                const int c = quarter * 32 + hh * 16 + u * 8 + T4;
+                                a1 = p.S1 ? __ldg(p.S1 + cls * 128 + c) : 0.f;
+                                a2 = p.S2 ? __ldg(p.S2 + cls * 128 + c) : 0.f;
+                            }
+                            float x = fmaf(in.x, __uint_as_float(acc[hh][pxo * 4 + u * 2 + e]), fmaf(-in.y, a1, a2));
+                            if (p.relu == 1) x = fmaxf(x, 0.f);
+                            if (p.residual) x += e ? bf16_hi(res[m]) : bf16_lo(res[m]);
+                            if (p.relu == 2) x = fmaxf(x, 0.f);
+                            v[e] = cls >= 0 ? x : 0.f;  // zero row / column of the ZP layout (and rows past the tensor, which TMA clips)
+                        }
+                        outp[m] = pack_bf16(v[0], v[1]);
+                        const float lo = bf16_lo(outp[m]), hi = bf16_hi(outp[m]);
+                        ps[pxo * 2] += lo;
+                        pss[pxo * 2] = fmaf(lo, lo, pss[pxo * 2]);
+                        ps[pxo * 2 + 1] += hi;
+                        pss[pxo * 2 + 1] = fmaf(hi, hi, pss[pxo * 2 + 1]);
+                    }
+                    stsm_x4_trans(maddr, outp);
+                }
+                if (p.stat_part) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float fb = inf[i].w;  // 0: first frame of the tile, 1: second
+                        sB = fmaf(fb, ps[i], sB);
+                        ssB = fmaf(fb, pss[i], ssB);
+                        sA = fmaf(1.f - fb, ps[i], sA);
+                        ssA = fmaf(1.f - fb, pss[i], ssA);
+                    }
+                }
+            }
+            fence_proxy_async();               // generic-proxy writes -> visible to the TMA store
+            named_bar_sync(1 + box, 64);       // both channel quarters of the box are in shared memory
+            if (leader_t) {
+                tma_store_2d(&tmO, stg, (quarter >> 1) * 64, (int)q0);  // rows >= Q are clipped
+                bulk_commit();
+                bulk_wait_read<0>();
+                setup_slot(tile + gridDim.x);
+            }
+            if (p.stat_part) {
+                sA = warp_sum(sA); ssA = warp_sum(ssA); sB = warp_sum(sB); ssB = warp_sum(ssB);
+                if (lane == 0) {
+                    float2* sp = reinterpret_cast<float2*>(p.stat_part) + ((size_t)tile * 8 + ew) * 2;
+                    sp[0] = make_float2(sA, ssA);
+                    sp[1] = make_float2(sB, ssB);
+                }
+            }
+        }
+        if (leader_t) bulk_wait_all<0>();
     } else {
         // ================= epilogue (warps 3..10) =================
         // The accumulator is transposed (TMEM lane = output channel, column = pixel).  Measured (tools/conv_bench.py history):
@@ -353,14 +536,32 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
     p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
     const uint32_t w_stage_bytes = 128 * kBlockK * 2;
-    const size_t tail = (4 + 2 * kCzMaxBStages + 4) * 8 + 16 + 2 * 64 * kCtPitch * 4 + 2 * 64 * 16 + 64;
+    // g_cz_swap: 1 = fragment epilogue (stmatrix + TMA store), 3 = the round-1 epilogue (A/B knob), 2 = debug (no epilogue work)
+    p.epi_mode = (g_cz_swap == 1 && ((uintptr_t)a->out & 127) == 0 && (!a->residual || ((uintptr_t)a->residual & 127) == 0)) ? 1 : 0;
+    const size_t bars_bytes = (4 + 2 * kCzMaxBStages + 4 + 4) * 8 + 16;
+    const size_t tail = p.epi_mode == 1 ? 65536 + bars_bytes + 2 * 2 * 128 * 16 + 64
+                                        : bars_bytes + 2 * 64 * kCtPitch * 4 + 2 * 64 * 16 + 64;
     const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - (long long)tail;
     int bst = (int)(budget / w_stage_bytes);
     if (bst > kCzMaxBStages) bst = kCzMaxBStages;
     VPT_CHECK(bst >= 2, "vpt_conv3x3_zp: not enough shared memory for the weight pipeline (W=%d)", W);
     p.b_stages = bst;
+    p.stage_off = 2 * p.a_stage_bytes + bst * (int)w_stage_bytes;
     const size_t smem_bytes = 1024 + 2 * (size_t)p.a_stage_bytes + (size_t)bst * w_stage_bytes + tail;
-    CUtensorMap tmX, tmW;
+    CUtensorMap tmX, tmW, tmO, tmR;
+    memset(&tmO, 0, sizeof(tmO));
+    memset(&tmR, 0, sizeof(tmR));
+    if (p.epi_mode == 1) {  // output / residual [Q][128] bf16: boxes of 128 pixel rows x 64 channels (128-byte rows, SWIZZLE_128B)
+        cuuint64_t dims[2] = {128, (cuuint64_t)p.Q};
+        cuuint64_t strides[1] = {256};
+        cuuint32_t box[2] = {64, 128};
+        int r = make_tmap_bf16(&tmO, a->out, 2, dims, strides, box);
+        if (r) return r;
+        if (a->residual) {
+            r = make_tmap_bf16(&tmR, a->residual, 2, dims, strides, box);
+            if (r) return r;
+        }
+    }
     {
         cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)p.Q};
         cuuint64_t strides[1] = {(cuuint64_t)C * 2};
@@ -388,9 +589,39 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     long long grid = num_sms();
     if (grid <= 0) grid = 148;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    conv3x3_zp_t_kernel<<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, p);
+    conv3x3_zp_t_kernel<<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
+}
+
+// epi_mode 1 statistics: mr[f] = (mean, rstd) of frame f from the per-(tile, warp, frame slot) partials; one warp per frame, fp64
+__global__ void __launch_bounds__(256) conv_zp_t_stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ mr, long long F, int FS,
+                                                                        long long num_tiles, double inv_count, float eps) {
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= F) return;
+    const int lane = threadIdx.x & 31;
+    const long long t0 = (f * FS) / kCtPix, t1 = min(num_tiles - 1, ((f + 1) * FS - 1) / kCtPix);
+    double s = 0.0, ss = 0.0;
+    for (long long i = lane; i < (t1 - t0 + 1) * 8; i += 32) {
+        const long long t = t0 + (i >> 3);
+        const long long slot = f - (t * kCtPix) / FS;  // which of the tile's (at most two) frames is f
+        if (slot == 0 || slot == 1) {
+            const float2 v = part[(t * 8 + (i & 7)) * 2 + slot];
+            s += (double)v.x;
+            ss += (double)v.y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+        const double mean = s * inv_count;
+        double var = ss * inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr[f] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
 }
 
 int g_cz_swap_enabled() { return g_cz_swap; }
@@ -400,5 +631,24 @@ int launch_conv_zp_t_fwd(const vpt_conv_zp_args* a, void* stream) { return launc
 
 extern "C" int vpt_set_conv_swap_mode(int32_t on) {
     vpt::g_cz_swap = on;  // 2 = debug: skip the epilogue arithmetic (MMA-rate experiment)
+    return VPT_OK;
+}
+
+/* Statistics plumbing of the fragment-epilogue kernel (Cout == 128): number of floats of its partial buffer ([tiles][8 warps][2 frame
+ * slots] float2), 0 when another kernel / epilogue handles this shape (then vpt_conv_zp_stat_parts + vpt_stats_finalize apply). */
+extern "C" int64_t vpt_conv_zp_t_stat_floats(int32_t F, int32_t H, int32_t W, int32_t Cout) {
+    if (Cout != 128 || vpt::g_cz_swap != 1) return 0;
+    const long long Q = (long long)F * (H + 1) * (W + 1);
+    return ((Q + vpt::kCtPix - 1) / vpt::kCtPix) * 8 * 2 * 2;
+}
+
+extern "C" int vpt_conv_zp_t_stats_finalize(const float* part, float* mr, int32_t F, int32_t H, int32_t W, float eps, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(part && mr && F > 0, "vpt_conv_zp_t_stats_finalize: null argument");
+    const int FS = (H + 1) * (W + 1);
+    const long long Q = (long long)F * FS, tiles = (Q + kCtPix - 1) / kCtPix;
+    conv_zp_t_stats_finalize_kernel<<<(unsigned)((F + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(part), reinterpret_cast<float2*>(mr), F, FS, tiles, 1.0 / ((double)H * W * 128), eps);
+    VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uin
 }  // namespace vpt
 
 extern "C" int vpt_firstconv_stat_parts(int32_t F, int32_t H, int32_t W, int32_t C0) {
-    if (vpt::firstconv_tc_applies(H, W)) return vpt::firstconv_tc_bands(F, H, (C0 + 127) / 128) * 2 * C0;  // per (band, half, channel)
+    if (vpt::firstconv_tc_applies(H, W)) return (H / 2 / vpt::kFtStatRows) * 2 * C0;  // per (8 pooled rows, column half, channel)
     return (H / 16) * (W / 16);
 }
 
@@ -222,9 +222,10 @@ extern "C" int vpt_set_firstconv_mode(int32_t mode) {
 }
 
 extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const float* bias, void* out, float* stat_part, int32_t F,
-                                  int32_t H, int32_t W, int32_t C0, int32_t zp, void* stream) {
+                                  int32_t H, int32_t W, int32_t C0, int32_t zp, int32_t out_f32, void* stream) {
     using namespace vpt;
     VPT_CHECK(img && w && bias && out && F > 0, "vpt_firstconv_pool: null argument");
+    VPT_CHECK(!out_f32 || firstconv_tc_applies(H, W), "vpt_firstconv_pool: fp32 output needs the tcgen05 kernel (W in {32,64,128}, H*W <= 16384)");
     VPT_CHECK(H % 16 == 0 && W % 16 == 0 && H >= 16 && W >= 16, "vpt_firstconv_pool: H, W must be multiples of 16 (H=%d W=%d)", H, W);
     VPT_CHECK(C0 == 64 || C0 == 128 || C0 == 192 || C0 == 256, "vpt_firstconv_pool: C0=%d not in {64,128,192,256}", C0);
     if (firstconv_tc_applies(H, W)) {
@@ -239,9 +240,14 @@ extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const floa
         p.nbands = firstconv_tc_bands(F, H, p.ncb);
         p.band_rows = (H / 2) / p.nbands;
         p.items = (long long)F * p.nbands * p.ncb;
-        if (W == 32) return launch_firstconv_tc<32>(p, stream);
-        if (W == 64) return launch_firstconv_tc<64>(p, stream);
-        return launch_firstconv_tc<128>(p, stream);
+        if (out_f32) {
+            if (W == 32) return launch_firstconv_tc<32, true>(p, stream);
+            if (W == 64) return launch_firstconv_tc<64, true>(p, stream);
+            return launch_firstconv_tc<128, true>(p, stream);
+        }
+        if (W == 32) return launch_firstconv_tc<32, false>(p, stream);
+        if (W == 64) return launch_firstconv_tc<64, false>(p, stream);
+        return launch_firstconv_tc<128, false>(p, stream);
     }
     const long long blocks = (long long)F * (H / 16) * (W / 16);
     VPT_CHECK(blocks < 2147483647LL, "vpt_firstconv_pool: too many tiles");

@@ -20,8 +20,10 @@
 //     operand tiles, double-buffered frames; the weights stay resident in shared memory.
 //
 //   warps 0..7: epilogue (quarter = warp % 4, column half = warp / 4)   warps 8..11: operand builders
-//   warp 12: MMA issuer (+ TMEM alloc)   warp 13: frame loader (cp.async.bulk)
+//   warp 12: MMA issuer (+ TMEM alloc)   (the first builder thread also issues the frame bulk copies, one item ahead)
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -29,7 +31,7 @@ namespace vpt {
 
 constexpr int kFtEpiWarps = 8;
 constexpr int kFtProdWarps = 4;
-constexpr int kFtThreads = 32 * (kFtEpiWarps + kFtProdWarps + 2);  // 448
+constexpr int kFtThreads = 32 * (kFtEpiWarps + kFtProdWarps + 1);  // 416
 constexpr int kFtMaxFrameBytes = 128 * 128 * 3;
 constexpr int kFtMaxBStages = 3;
 
@@ -38,7 +40,7 @@ struct FirstconvTcParams {
     const float* w;      // [C0][27] (ky, kx, c), already / 255
     const float* bias;   // [C0]
     __nv_bfloat16* out;
-    float2* stat_part;   // [F][P] with P = nbands * 2 * C0: index (band * 2 + half) * C0 + channel
+    float2* stat_part;   // [F][P] with P = (H/2/8) * 2 * C0: index ((pooled row / 8) * 2 + half) * C0 + channel
     int H, C0, zp;
     int ncb;             // 128-channel blocks
     int nbands, band_rows;  // pooled rows per band
@@ -112,10 +114,48 @@ __device__ __forceinline__ FtItem ft_item(const FirstconvTcParams& p, long long 
     return it;
 }
 
-template <int W>
+
+constexpr int kFtStatRows = 8;  // pooled rows per statistics partial (fixed, so that the partial sums do not depend on the band split)
+
+// One epilogue chunk: CW conv columns of the two conv rows of a tile (a = row 2t, b = row 2t+1) -> CW/2 pooled outputs of pooled row t.
+//   la / lb: conv column to the left of the chunk (in: previous chunk's last column; out: this chunk's last column)
+//   carry:   horizontally pooled row 2t-1 (in) / 2t+1 (out)
+// EMIT = false only primes the carry (first tile of a later band).
+template <int CW, bool F32OUT, bool EMIT>
+__device__ __forceinline__ void ft_pool_chunk(const float (&a)[CW], const float (&b)[CW], float& la, float& lb, float (&carry)[CW / 2], void* optr,
+                                              size_t stride, bool valid, float& st_s, float& st_ss) {
+    using OutT = typename std::conditional<F32OUT, float, __nv_bfloat16>::type;
+    OutT* op = reinterpret_cast<OutT*>(optr);
+#pragma unroll
+    for (int k = 0; k < CW / 2; ++k) {
+        const float pa = (k == 0) ? la : a[2 * k - 1], pb = (k == 0) ? lb : b[2 * k - 1];
+        const float m0 = fmaxf(fmaxf(pa, a[2 * k]), a[2 * k + 1]);        // conv row 2t
+        const float m1 = fmaxf(fmaxf(pb, b[2 * k]), b[2 * k + 1]);        // conv row 2t + 1
+        if (EMIT) {
+            const float o = fmaxf(fmaxf(fmaxf(carry[k], m0), m1), 0.f);   // rows 2t-1, 2t, 2t+1 ; ReLU after the max
+            float of = o;
+            if (F32OUT) {
+                if (valid) *reinterpret_cast<float*>(op) = o;
+            } else {
+                const __nv_bfloat16 ob = __float2bfloat16_rn(o);
+                if (valid) *reinterpret_cast<__nv_bfloat16*>(op) = ob;
+                of = __bfloat162float(ob);
+            }
+            st_s += of;
+            st_ss = fmaf(of, of, st_ss);
+            op += stride;
+        }
+        carry[k] = m1;
+    }
+    la = a[CW - 1];
+    lb = b[CW - 1];
+}
+
+template <int W, bool F32OUT>
 __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const FirstconvTcParams p) {
     constexpr int NPOS = 2 * W;           // UMMA N: two conv rows
-    constexpr int CW = W / 4;             // columns per epilogue chunk (two chunks per warp and row)
+    constexpr int CW = 16;                // columns per epilogue chunk
+    constexpr int NCH = W / 32;           // chunks per epilogue warp and conv row (the warp owns W/2 columns)
     constexpr int PITCH = W * 3;          // bytes per frame row
     constexpr uint32_t kBStage = NPOS * 128;
     extern __shared__ uint8_t smem_raw[];
@@ -189,23 +229,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const First
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 13) {
-        // ================= frame loader: the rows a band needs, one bulk copy per item =================
-        if (lane == 0) {
-            int li = 0;
-            bool ok = true;
-            for (long long item = blockIdx.x; item < p.items && ok; item += gridDim.x, ++li) {
-                const FtItem it = ft_item(p, item);
-                const int buf = li & 1;
-                if (!(ok = mbar_wait(&fr_empty[buf], (uint32_t)((li >> 1) & 1) ^ 1u, 0x910u))) break;
-                const int r0 = max(0, 2 * it.t0 - 1), r1 = min(H, 2 * it.t1 + 3);  // input rows [r0, r1)
-                const uint32_t bytes = (uint32_t)(r1 - r0) * PITCH;
-                mbar_expect_tx(&fr_full[buf], bytes);
-                bulk_copy_g2s(s_frames + (size_t)buf * p.frame_stride + 16 + (size_t)r0 * PITCH, p.img + (size_t)it.f * H * PITCH + (size_t)r0 * PITCH, bytes,
-                              &fr_full[buf]);
-            }
-        }
-    } else if (warp == 12) {
+    if (warp == 12) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, NPOS);
@@ -237,9 +261,24 @@ __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const First
         int stage = 0, li = 0;
         uint32_t phase = 0;
         bool ok = true;
+        // frame loader (builder thread 0): the rows a band needs, one bulk copy per item, requested one item ahead
+        auto request_frame = [&](long long item, int lj) {
+            const FtItem it = ft_item(p, item);
+            const int buf = lj & 1;
+            if (!mbar_wait(&fr_empty[buf], (uint32_t)((lj >> 1) & 1) ^ 1u, 0x910u)) return false;
+            const int r0 = max(0, 2 * it.t0 - 1), r1 = min(H, 2 * it.t1 + 3);  // input rows [r0, r1)
+            const uint32_t bytes = (uint32_t)(r1 - r0) * PITCH;
+            mbar_expect_tx(&fr_full[buf], bytes);
+            bulk_copy_g2s(s_frames + (size_t)buf * p.frame_stride + 16 + (size_t)r0 * PITCH, p.img + (size_t)it.f * H * PITCH + (size_t)r0 * PITCH, bytes,
+                          &fr_full[buf]);
+            return true;
+        };
+        if (tp == 0 && (long long)blockIdx.x < p.items) ok = request_frame(blockIdx.x, 0);
         for (long long item = blockIdx.x; item < p.items && ok; item += gridDim.x, ++li) {
             const FtItem it = ft_item(p, item);
             const int buf = li & 1;
+            if (tp == 0 && item + gridDim.x < p.items) request_frame(item + gridDim.x, li + 1);
+            __syncwarp();
             if (!(ok = mbar_wait(&fr_full[buf], (uint32_t)(li >> 1) & 1u, 0x930u))) break;
             const uint8_t* fr = s_frames + (size_t)buf * p.frame_stride + 16;
             for (int t = it.t0; t <= it.t1 && ok; ++t) {
@@ -294,73 +333,65 @@ __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const First
         }
     } else {
         // ================= epilogue (warps 0..7): thread = output channel; pooling in registers =================
+        using OutT = typename std::conditional<F32OUT, float, __nv_bfloat16>::type;
         const int quarter = warp & 3, half = warp >> 2;
         const int x0 = half * (W / 2);          // this warp's conv columns [x0, x0 + W/2)
         const int Ho = H / 2, Wo = W / 2;
         const int opitch = Wo + p.zp;
+        const size_t cstride = (size_t)p.C0;    // elements between pooled columns
+        OutT* const outp = reinterpret_cast<OutT*>(p.out);
+        const int sgroups = Ho / kFtStatRows;   // statistics partials per frame and (half, channel)
         int local = 0;
         bool ok = true;
         for (long long item = blockIdx.x; item < p.items && ok; item += gridDim.x) {
             const FtItem it = ft_item(p, item);
             const int ch = it.cb * 128 + quarter * 32 + lane;
             const bool valid = ch < p.C0;
-            __nv_bfloat16* fout = p.out + (size_t)it.f * (Ho + p.zp) * opitch * p.C0 + ch;
-            float carry[2][CW / 2];
+            OutT* const fout = outp + (size_t)it.f * (Ho + p.zp) * opitch * p.C0 + ch;  // (frame, row 0, col 0, ch)
+            float2* const fstat = p.stat_part ? p.stat_part + (size_t)it.f * (sgroups * 2 * p.C0) + (size_t)half * p.C0 + ch : nullptr;
+            float carry[NCH][CW / 2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int j = 0; j < NCH; ++j)
 #pragma unroll
                 for (int k = 0; k < CW / 2; ++k) carry[j][k] = 0.f;
             float st_s = 0.f, st_ss = 0.f;
             for (int t = it.t0; t <= it.t1 && ok; ++t, ++local) {
                 const int as = local & 1;
-                const bool emit = (t >= it.band * p.band_rows) && valid;  // the first tile of a later band only primes the carry
+                const bool emit = t >= it.band * p.band_rows;  // the first tile of a later band only primes the carry
                 if (!(ok = mbar_wait(&tmem_full_bar[as], (uint32_t)(local >> 1) & 1u, 0x940u))) break;
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols);
                 float la = 0.f, lb = 0.f;  // conv column x0 - 1 (0 stands for "outside": every result is max'ed with 0 by the ReLU)
-                if (half == 1) {
-                    la = tmem_ld_col1(trow + x0 - 1);
-                    lb = tmem_ld_col1(trow + W + x0 - 1);
-                }
-                __nv_bfloat16* orow = fout + (size_t)t * opitch * p.C0;
+                OutT* orow = fout + ((size_t)t * opitch + x0 / 2) * cstride;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < NCH; ++j) {
                     float a[CW], b[CW];
                     tmem_ld_cols<CW>(trow + x0 + j * CW, a);
                     tmem_ld_cols<CW>(trow + W + x0 + j * CW, b);
+                    if (j == 0 && half == 1) {
+                        la = tmem_ld_col1(trow + x0 - 1);
+                        lb = tmem_ld_col1(trow + W + x0 - 1);
+                    }
                     tmem_ld_wait();
-                    if (j == 1) {  // the accumulator stage is in registers: hand it back to the MMA warp
+                    if (j == NCH - 1) {  // the accumulator stage is in registers: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                     }
-#pragma unroll
-                    for (int k = 0; k < CW / 2; ++k) {
-                        const float pa = (k == 0) ? la : a[2 * k - 1], pb = (k == 0) ? lb : b[2 * k - 1];
-                        const float m0 = fmaxf(fmaxf(pa, a[2 * k]), a[2 * k + 1]);   // conv row 2t
-                        const float m1 = fmaxf(fmaxf(pb, b[2 * k]), b[2 * k + 1]);   // conv row 2t + 1
-                        const float o = fmaxf(fmaxf(fmaxf(carry[j][k], m0), m1), 0.f);  // rows 2t-1, 2t, 2t+1 ; ReLU after the max
-                        carry[j][k] = m1;
-                        if (emit) {
-                            const __nv_bfloat16 ob = __float2bfloat16_rn(o);
-                            orow[(size_t)((x0 + j * CW) / 2 + k) * p.C0] = ob;
-                            const float of = __bfloat162float(ob);
-                            st_s += of;
-                            st_ss = fmaf(of, of, st_ss);
-                        }
+                    if (emit) ft_pool_chunk<CW, F32OUT, true>(a, b, la, lb, carry[j], orow + (size_t)j * (CW / 2) * cstride, cstride, valid, st_s, st_ss);
+                    else ft_pool_chunk<CW, F32OUT, false>(a, b, la, lb, carry[j], orow, cstride, valid, st_s, st_ss);
+                }
+                if (emit && valid) {
+                    if (p.zp && half == 1) fout[((size_t)t * opitch + Wo) * cstride] = OutT(0.f);  // zero column of the ZP layout
+                    if (fstat && (t % kFtStatRows) == kFtStatRows - 1) {                            // one partial per 8 pooled rows
+                        fstat[(size_t)(t / kFtStatRows) * 2 * p.C0] = make_float2(st_s, st_ss);
+                        st_s = st_ss = 0.f;
                     }
-                    la = a[CW - 1];
-                    lb = b[CW - 1];
                 }
-                if (emit && p.zp && half == 1) orow[(size_t)Wo * p.C0] = __float2bfloat16_rn(0.f);  // zero column of the ZP layout
             }
-            if (ok && valid) {
-                if (p.zp && it.band == p.nbands - 1) {  // zero row y = Ho (+ the corner)
-                    __nv_bfloat16* zrow = fout + (size_t)Ho * opitch * p.C0;
-                    for (int px = x0 / 2; px < x0 / 2 + W / 4 + (half == 1 ? 1 : 0); ++px) zrow[(size_t)px * p.C0] = __float2bfloat16_rn(0.f);
-                }
-                if (p.stat_part)
-                    p.stat_part[(size_t)it.f * (p.nbands * 2 * p.C0) + (size_t)(it.band * 2 + half) * p.C0 + ch] = make_float2(st_s, st_ss);
+            if (ok && valid && p.zp && it.band == p.nbands - 1) {  // zero row y = Ho (+ the corner)
+                OutT* zrow = fout + (size_t)Ho * opitch * cstride;
+                for (int px = x0 / 2; px < x0 / 2 + W / 4 + (half == 1 ? 1 : 0); ++px) zrow[(size_t)px * cstride] = OutT(0.f);
             }
         }
     }
@@ -379,14 +410,15 @@ static int firstconv_tc_bands(long long F, int H, int ncb) {
     const int Ho = H / 2;
     int nb = 1;
     const long long target = 2LL * (num_sms() > 0 ? num_sms() : 148);
-    while (F * ncb * nb < target && Ho % (nb * 2) == 0 && Ho / (nb * 2) >= 2) nb *= 2;
+    // bands hold whole 8-row statistics groups, so the partial sums (hence the results, bit for bit) do not depend on the split
+    while (F * ncb * nb < target && Ho % (nb * 2 * kFtStatRows) == 0) nb *= 2;
     return nb;
 }
 static bool firstconv_tc_applies(int H, int W) {
     return g_fc_mode == 1 && (W == 32 || W == 64 || W == 128) && (long long)H * W * 3 <= kFtMaxFrameBytes && H % 2 == 0;
 }
 
-template <int W>
+template <int W, bool F32OUT>
 static int launch_firstconv_tc(const FirstconvTcParams& p0, void* stream) {
     FirstconvTcParams p = p0;
     const int pitch = W * 3;
@@ -400,12 +432,12 @@ static int launch_firstconv_tc(const FirstconvTcParams& p0, void* stream) {
     const size_t smem = fixed + bst * bstage;
     static size_t attr = 0;
     if (smem > attr) {
-        VPT_CUDA(cudaFuncSetAttribute(firstconv_tc_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VPT_CUDA(cudaFuncSetAttribute(firstconv_tc_kernel<W, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     long long grid = num_sms() > 0 ? num_sms() : 148;
     if (grid > p.items) grid = p.items;
-    firstconv_tc_kernel<W><<<(unsigned)grid, kFtThreads, smem, (cudaStream_t)stream>>>(p);
+    firstconv_tc_kernel<W, F32OUT><<<(unsigned)grid, kFtThreads, smem, (cudaStream_t)stream>>>(p);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

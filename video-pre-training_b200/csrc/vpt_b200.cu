@@ -31,6 +31,8 @@ void set_error(const char* fmt, ...) {
 #include "backward.cuh"
 #include "attention_bwd.cuh"
 #include "firstconv_bwd.cuh"
+#include "precise.cuh"
+#include "codec.cuh"
 
 extern "C" const char* vpt_last_error(void) { return vpt::g_err; }
 extern "C" int vpt_abi_version(void) { return VPT_ABI_VERSION; }

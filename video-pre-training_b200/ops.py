@@ -91,7 +91,10 @@ def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None,
         out = torch.empty((F_, H + 1, W + 1, Cout), dtype=BF16, device=x.device)
     assert out.is_contiguous() and tuple(out.shape) == (F_, H + 1, W + 1, Cout)
     P = nat.lib().vpt_conv_zp_stat_parts(Cout)
-    part = torch.empty((F_ * (H + 1) * (W + 1), P, 2), dtype=F32, device=x.device) if want_stats else None
+    tfl = nat.lib().vpt_conv_zp_t_stat_floats(F_, H, W, Cout)  # > 0: the swapped kernel's fragment epilogue (per-tile partials)
+    part = None
+    if want_stats:
+        part = torch.empty((tfl,) if tfl > 0 else (F_ * (H + 1) * (W + 1), P, 2), dtype=F32, device=x.device)
     a = nat.ConvZpArgs()
     a.x, a.w, a.F, a.H, a.W, a.Cin, a.Cout = _p(x), _p(Wb), F_, H, W, Cin, Cout
     a.mr, a.S1, a.S2, a.relu, a.residual, a.out, a.stat_part = _p(mr), _p(S1), _p(S2), relu, _p(residual), _p(out), _p(part)
@@ -104,33 +107,94 @@ def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None,
         e1.record()
         prof.append((e0, e1, 2.0 * F_ * H * W * Cout * 9 * Cin, "conv", (F_ * H * W, Cout, 9 * Cin)))  # algorithmic FLOPs (no halo rows)
     _count()
-    mr_out = stats_finalize(part, F_, (H + 1) * (W + 1) * P, H * W * Cout) if want_stats else None
+    mr_out = None
+    if want_stats and tfl > 0:
+        mr_out = torch.empty((F_, 2), dtype=F32, device=x.device)
+        nat.check(nat.lib().vpt_conv_zp_t_stats_finalize(_p(part), _p(mr_out), F_, H, W, 1e-5, _stream()), "vpt_conv_zp_t_stats_finalize")
+        _count()
+    elif want_stats:
+        mr_out = stats_finalize(part, F_, (H + 1) * (W + 1) * P, H * W * Cout)
     return out, mr_out
 
 
-def firstconv_pool(img, w, bias, C0, zp=True):
-    """img u8 [F,H,W,3] -> (bf16 [F,H/2(+1),W/2(+1),C0] (ZP layout when zp), per-frame (mean, rstd))."""
+def firstconv_pool(img, w, bias, C0, zp=True, out_f32=False):
+    """img u8 [F,H,W,3] -> (bf16 (fp32 with out_f32) [F,H/2(+1),W/2(+1),C0] (ZP layout when zp), per-frame (mean, rstd))."""
     _cuda(img, w, bias)
     F_, H, W, _ = img.shape
     z = int(zp)
-    out = torch.empty((F_, H // 2 + z, W // 2 + z, C0), dtype=BF16, device=img.device)
+    out = torch.empty((F_, H // 2 + z, W // 2 + z, C0), dtype=F32 if out_f32 else BF16, device=img.device)
     P = nat.lib().vpt_firstconv_stat_parts(F_, H, W, C0)
     part = torch.empty((F_, P, 2), dtype=F32, device=img.device)
-    nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, z, _stream()), "vpt_firstconv_pool")
+    nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, z, int(out_f32), _stream()), "vpt_firstconv_pool")
     _count()
     return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * C0)
 
 
-def conv3d_t5(img, w, bias, C):
-    """img u8 [B,T,H,W,3] -> (bf16 ZP [B*T,H+1,W+1,C], per-frame (mean, rstd)); lib/policy.py:394-403."""
+def conv3d_t5(img, w, bias, C, out_f32=False):
+    """img u8 [B,T,H,W,3] -> (bf16 (fp32 with out_f32) ZP [B*T,H+1,W+1,C], per-frame (mean, rstd)); lib/policy.py:394-403."""
     _cuda(img, w, bias)
     B, T, H, W, _ = img.shape
-    out = torch.empty((B * T, H + 1, W + 1, C), dtype=BF16, device=img.device)
+    out = torch.empty((B * T, H + 1, W + 1, C), dtype=F32 if out_f32 else BF16, device=img.device)
     P = nat.lib().vpt_conv3d_stat_parts(H, W, C)
     part = torch.empty((B * T, P, 2), dtype=F32, device=img.device)
-    nat.check(nat.lib().vpt_conv3d_t5(_p(img), _p(w), _p(bias), _p(out), _p(part), B, T, H, W, C, _stream()), "vpt_conv3d_t5")
+    nat.check(nat.lib().vpt_conv3d_t5(_p(img), _p(w), _p(bias), _p(out), _p(part), B, T, H, W, C, int(out_f32), _stream()), "vpt_conv3d_t5")
     _count()
     return out, stats_finalize(part, B * T, P, H * W * C)
+
+
+# ---- fp32-parity precision mode (csrc/precise.cuh) ----------------------------------------------------------------------
+def group_stats_f32(x, groups, eps=1e-5):
+    """(mean, rstd) [groups, 2] over equal consecutive slices of the fp32 tensor x."""
+    _cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.numel() % groups == 0
+    mr = torch.empty((groups, 2), dtype=F32, device=x.device)
+    nat.check(nat.lib().vpt_group_stats_f32(_p(x), _p(mr), groups, x.numel() // groups, eps, _stream()), "vpt_group_stats_f32")
+    _count()
+    return mr
+
+
+def norm_split_f32(x, mr=None, gamma=None, beta=None, groups=1, split=True, want_f32=False):
+    """u = [(x - mean_g) rstd_g] gamma[c] + beta[c] on fp32 x [..., C] -> (hi bf16, lo bf16, u fp32) (None where not requested)."""
+    _cuda(x, mr, gamma, beta)
+    assert x.dtype == F32 and x.is_contiguous()
+    C = x.shape[-1]
+    hi = torch.empty(x.shape, dtype=BF16, device=x.device) if split else None
+    lo = torch.empty(x.shape, dtype=BF16, device=x.device) if split else None
+    u = torch.empty_like(x) if want_f32 else None
+    nat.check(nat.lib().vpt_norm_split_f32(_p(x), _p(mr), _p(gamma), _p(beta), _p(hi), _p(lo), _p(u), x.numel(), C, x.numel() // groups, _stream()),
+              "vpt_norm_split_f32")
+    _count()
+    return hi, lo, u
+
+
+def add_f32(a, b=None, relu=False, out=None):
+    _cuda(a, b)
+    assert a.dtype == F32 and a.is_contiguous() and (b is None or (b.dtype == F32 and b.is_contiguous() and b.shape == a.shape))
+    if out is None:
+        out = torch.empty_like(a)
+    nat.check(nat.lib().vpt_add_f32(_p(a), _p(b), _p(out), a.numel(), int(relu), _stream()), "vpt_add_f32")
+    _count()
+    return out
+
+
+def maxpool3s2_f32(x):
+    """fp32 NHWC [F,H,W,C] -> [F,H/2,W/2,C] (max_pool2d(3, 2, 1))."""
+    _cuda(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    F_, H, W, Cc = x.shape
+    out = torch.empty((F_, H // 2, W // 2, Cc), dtype=F32, device=x.device)
+    nat.check(nat.lib().vpt_maxpool3s2_f32(_p(x), _p(out), F_, H, W, Cc, _stream()), "vpt_maxpool3s2_f32")
+    _count()
+    return out
+
+
+def attention_f32(q, full_k, full_v, R, b_nd, first_u8, smask_u8, B, t, maxlen, heads, causal=True):
+    _cuda(q, full_k, full_v)
+    out = torch.empty_like(q)
+    nat.check(nat.lib().vpt_attention_f32(_p(q), _p(full_k), _p(full_v), _p(R), _p(b_nd), _p(first_u8), _p(smask_u8), _p(out), B, t, maxlen, heads,
+                                          int(causal), _stream()), "vpt_attention_f32")
+    _count()
+    return out
 
 
 def maxpool3s2(x, zp=True):
@@ -396,5 +460,29 @@ def softmax_bwd(logp, idx, scale, out, col0):
     rows, n = logp.shape
     nat.check(nat.lib().vpt_softmax_bwd(_p(logp.contiguous()), _p(idx.contiguous()), float(scale), _p(out), out.stride(0), col0, rows, n, _stream()),
               "vpt_softmax_bwd")
+    _count()
+    return out
+
+
+# ---- on-device action codec (csrc/codec.cuh) -----------------------------------------------------------------------------
+def codec_to_env(buttons, camera, lut_btn, lut_cam_off, cam_lut, nbins):
+    """int64 [n] joint indices -> int64 [n, 22] words (20 button flags + 2 float64 camera angles as bit patterns)."""
+    _cuda(buttons, camera, lut_btn, lut_cam_off, cam_lut)
+    n = buttons.numel()
+    out = torch.empty((n, 22), dtype=torch.int64, device=buttons.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=buttons.device)
+    nat.check(nat.lib().vpt_codec_to_env(_p(buttons), _p(camera), _p(lut_btn), _p(lut_cam_off), _p(cam_lut), nbins, lut_cam_off.numel(), n, _p(out), _p(bad),
+                                         _stream()), "vpt_codec_to_env")
+    _count()
+    return out, bad
+
+
+def codec_from_env(buttons, camera, thresholds, nbins, strides, inventory_idx):
+    """int64 [n, 20] button flags + float64 [n, 2] camera angles -> int64 [n, 3] (buttons index, camera index, is-null flag)."""
+    _cuda(buttons, camera, thresholds, strides)
+    n = buttons.shape[0]
+    out = torch.empty((n, 3), dtype=torch.int64, device=buttons.device)
+    nat.check(nat.lib().vpt_codec_from_env(_p(buttons), _p(camera), _p(thresholds), nbins, _p(strides), inventory_idx, n, _p(out), _stream()),
+              "vpt_codec_from_env")
     _count()
     return out

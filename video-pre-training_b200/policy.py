@@ -327,6 +327,9 @@ class MinecraftPolicy(nn.Module):
             _set(self, name, t)
         self._prep = None
         self._prep_fp = None
+        self.precision = "bf16"  # "fp32": the fp32-parity mode (precise.py): bf16 hi/lo split operands, fp32 activations
+        self._pprep = None
+        self._pprep_fp = None
         self.debug_taps = None  # set to a dict to capture intermediate activations (tests)
         self._tape = None       # set to a dict by training.BCTrainer: the forward then records what the backward needs
 
@@ -347,6 +350,15 @@ class MinecraftPolicy(nn.Module):
                 self._prep = _Prepared(self.cfg, dict(self.named_parameters()))
             self._prep_fp = fp
         return self._prep
+
+    def prepared_precise(self):
+        from .precise import PreparedPrecise
+        fp = _fingerprint(self)
+        if self._pprep is None or fp != self._pprep_fp:
+            with torch.no_grad():
+                self._pprep = PreparedPrecise(self.cfg, dict(self.named_parameters()))
+            self._pprep_fp = fp
+        return self._pprep
 
     def _tap(self, name, t):
         if self.debug_taps is not None:
@@ -472,6 +484,13 @@ class MinecraftPolicy(nn.Module):
         assert tuple(img.shape[2:]) == frame_shape, f"img shape {tuple(img.shape[2:])} != {frame_shape}"
         assert len(state_in) == cfg.n_layers, \
             f"Length of state {len(state_in)} did not match length of blocks {cfg.n_layers}"  # lib/util.py:117-119
+        if self.precision == "fp32":
+            if self._tape is not None:
+                raise NotImplementedError("the BC step runs in the bf16 mode only")
+            from . import precise
+            return precise.forward(self, img, first, state_in, use_lastlayer)
+        if self.precision != "bf16":
+            raise ValueError(f"unknown precision {self.precision!r} (use 'bf16' or 'fp32')")
         prep = self.prepared()
         N = B * t
         frames = img.reshape(N, *frame_shape).contiguous()
@@ -579,6 +598,32 @@ class _PolicyBase(nn.Module):
     def initial_state(self, batch_size: int):
         return self.net.initial_state(batch_size)
 
+    def set_precision(self, precision: str):
+        """"bf16" (default, production: bf16 operands, 1e-2 tolerance) or "fp32" (fp32-parity mode, precise.py: 1e-3 tolerance)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.net.precision = precision
+        return self
+
+    def _heads_prepared_precise(self):
+        from .precise import _f, _split_w
+        params = [p for n, p in self.named_parameters() if not n.startswith("net.")]
+        fp = tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, "_hpprep", None) is None or fp != self._hpprep_fp:
+            with torch.no_grad():
+                ws, bs, cols, c0 = [], [], OrderedDict(), 0
+                for name in self.head_specs:
+                    lin = getattr(self.pi_head, name).linear_layer
+                    ws.append(lin.weight.detach())
+                    bs.append(lin.bias.detach())
+                    cols[name] = (c0, lin.weight.shape[0])
+                    c0 += lin.weight.shape[0]
+                self._hpprep = dict(pi=(_split_w(torch.cat(ws, 0)), _f(torch.cat(bs, 0))), cols=cols, ntot=c0)
+                if self.has_value_head:
+                    self._hpprep["v"] = (_split_w(self.value_head.linear.weight), _f(self.value_head.linear.bias))
+            self._hpprep_fp = fp
+        return self._hpprep
+
     def _heads_prepared(self):
         params = [p for n, p in self.named_parameters() if not n.startswith("net.")]
         fp = tuple((p.data_ptr(), p._version) for p in params)
@@ -600,6 +645,9 @@ class _PolicyBase(nn.Module):
     @torch.no_grad()
     def _heads(self, lat_bf16, B, t, mask=None):
         """lib/action_head.py:163-174 for every head + lib/scaled_mse_head.py:34-35."""
+        if isinstance(lat_bf16, tuple):  # fp32-parity mode: (latent hi, latent lo)
+            from . import precise
+            return precise.heads(self, lat_bf16, B, t, mask)
         hp = self._heads_prepared()
         N = lat_bf16.shape[0]
         ntot = hp["ntot"]
