@@ -77,6 +77,17 @@ typedef struct vpt_gemm_args {
     float* stat_part;         /* NULL or float2 partials of the stored values (see stat_mode) */
     int32_t stat_mode;        /* 1: [M][P] per row;  2: [ceil(M/32)][P] per 32 rows;  P = vpt_gemm_stat_parts(N) */
     int32_t cluster;          /* CTAs per thread-block cluster sharing the B tile by TMA multicast: 0 = default, 1, 2, 4 */
+    /* Column segments (fused projections, e.g. Q | K | V | R of lib/xf.py:334-365 as ONE GEMM over the concatenated weight): columns
+     * [dst_n0[i], dst_n0[i+1]) go to dst_out[i] (column 0 of that buffer = column dst_n0[i] of the GEMM) with its own leading dimension
+     * and dtype; dst_remap[i] != 0 applies the seg_len / seg_stride / seg_off row remap to that segment only.  ndst == 0: out / ld_out /
+     * out_f32 (+ the row remap, if any) describe the single destination.  Every dst_n0[i] must be a multiple of the N tile (256 for
+     * N > 256); statistics partials are not supported with segments. */
+    int32_t ndst;
+    int32_t dst_n0[4];
+    void* dst_out[4];
+    int64_t dst_ld[4];
+    int32_t dst_f32[4];
+    int32_t dst_remap[4];
 } vpt_gemm_args;
 
 int vpt_gemm_bf16(const vpt_gemm_args* args, void* stream);
@@ -120,7 +131,7 @@ int vpt_set_conv_pair_mode(int32_t on);
  * csrc/conv_zp_t.cuh); 0: the regular orientation.  Changes vpt_conv_zp_stat_parts(128).  Tuning / A-B knob. */
 int vpt_set_conv_swap_mode(int32_t on);
 int vpt_conv_zp_stat_parts(int32_t Cout);
-/* Cout == 128 with the operand-swapped kernel's fragment epilogue (default): its statistics partials are per (tile, warp, frame slot),
+/* Cout == 128 with the operand-swapped kernel's experimental fragment epilogue (vpt_set_conv_swap_mode(4)): its statistics partials are per (tile, warp, frame slot),
  * not per row.  vpt_conv_zp_t_stat_floats > 0 <=> pass a float buffer of that many elements as stat_part and finalise it with
  * vpt_conv_zp_t_stats_finalize (mr[f] = mean, rstd over the H*W*128 interior values of frame f). */
 int64_t vpt_conv_zp_t_stat_floats(int32_t F, int32_t H, int32_t W, int32_t Cout);

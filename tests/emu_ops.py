@@ -29,7 +29,16 @@ def _row_stats(v, rows_per_group):
 
 
 def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, S2=None, relu=0, out_scale=1.0,
-         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0, cluster=0):
+         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0, cluster=0, dsts=None):
+    if dsts:  # column segments with their own destination: emulate as one GEMM per segment
+        assert stat_part is None
+        bounds = [d[0] for d in dsts] + [N]
+        for i, (n0, t, ld, remap) in enumerate(dsts):
+            n1 = bounds[i + 1]
+            sl = lambda v: None if v is None else v.reshape(-1, N)[:, n0:n1].contiguous()
+            gemm(A, Bw[n0:n1], t, M, n1 - n0, K, conv=conv, mr=mr, rows_per_group=rows_per_group, S1=sl(S1), S2=sl(S2), relu=relu,
+                 out_scale=out_scale, residual=residual, ld_out=ld, seg=seg if remap else None)
+        return out
     Af = A.float()
     if conv is not None:
         H, W, Cin = conv

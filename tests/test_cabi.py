@@ -51,7 +51,7 @@ def test_gemm_args_struct_layout_matches_header():
         if not decl:
             continue
         names = decl.replace("*", " ").split()
-        fields += [n.strip(",") for n in decl.replace("*", " ").replace(",", " ").split()[(2 if names[0] == "const" else 1):]]
+        fields += [re.sub(r"\[\d+\]", "", n.strip(",")) for n in decl.replace("*", " ").replace(",", " ").split()[(2 if names[0] == "const" else 1):]]
     assert fields == [f[0] for f in nat.GemmArgs._fields_], (fields, [f[0] for f in nat.GemmArgs._fields_])
 
 

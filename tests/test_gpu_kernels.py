@@ -128,7 +128,7 @@ def test_gemm_conv3x3(H, W, Cin, Cout, F_):
 
 @pytest.mark.parametrize("H,W,Cin,Cout,F_", [(16, 16, 64, 64, 3), (8, 8, 128, 128, 5), (4, 4, 128, 128, 11), (32, 32, 128, 256, 2),
                                              (64, 64, 128, 128, 3), (64, 64, 128, 256, 1), (16, 16, 256, 256, 3), (32, 32, 192, 384, 1),
-                                             (32, 32, 256, 256, 7)])
+                                             (32, 32, 256, 256, 7), (16, 16, 128, 128, 9)])
 def test_conv3x3_zp(H, W, Cin, Cout, F_):
     """ZP-layout conv with the input span reused across the 9 taps (shifted UMMA descriptors) vs F.conv2d + fold."""
     g = torch.Generator().manual_seed(13)
@@ -139,7 +139,8 @@ def test_conv3x3_zp(H, W, Cin, Cout, F_):
     res = E.to_zp(_rand((F_, H, W, Cout), g))
     try:
         # pair: one CTA per tile / SM pairs with tcgen05.mma.cta_group::2; swap: operand-swapped kernel for Cout == 128
-        for pair, swap in ((0, 0), (2, 0), (0, 1)) if Cout == 128 else ((0, 0), (2, 0)):
+        # swap 4: the experimental fragment epilogue (tcgen05.ld.16x256b -> stmatrix.trans -> TMA store; falls back below 256 rows / frame)
+        for pair, swap in ((0, 0), (2, 0), (0, 1), (0, 4)) if Cout == 128 else ((0, 0), (2, 0), (0x100, 0), (0x102, 0)):
             nat.lib().vpt_set_conv_pair_mode(pair)
             nat.lib().vpt_set_conv_swap_mode(swap)
             for residual in (None, res):
@@ -312,3 +313,31 @@ def test_fused_adam_matches_torch_optim():
     nat.device_check()
     for p, q in zip(ref_params, our_params):
         assert torch.allclose(q.detach().cpu(), p.detach(), rtol=1e-5, atol=1e-7), (q.detach().cpu() - p.detach()).abs().max()
+
+
+def test_gemm_column_segments_fused_qkvr():
+    """vpt_gemm_args.dst_*: ONE GEMM over the concatenated Q | K | V | R weight writes each column segment to its own destination
+    (bf16 q; K / V into the rows after the memory of the [B][maxlen + t][h] buffers through the row remap; R in fp32) == four GEMMs."""
+    g = torch.Generator().manual_seed(31)
+    for (B, t, maxlen, h, heads) in [(3, 8, 16, 256, 2), (2, 128, 128, 1024, 8)]:
+        M, T, nr = B * t, maxlen + t, 10 * heads
+        x = _rand((M, h), g)
+        Wc = _rand((3 * h + nr, h), g, h ** -0.5)
+        bias = torch.randn(3 * h + nr, generator=g)
+
+        def run(mod, dev):
+            to = lambda v: v.to(dev)
+            q = torch.zeros((M, h), dtype=BF16, device=dev)
+            fk = torch.zeros((B, T, h), dtype=BF16, device=dev)
+            fv = torch.zeros((B, T, h), dtype=BF16, device=dev)
+            R = torch.zeros((M, nr), dtype=F32, device=dev)
+            mod.gemm(to(x), to(Wc), q, M, 3 * h + nr, h, S2=to(bias), seg=(t, T, maxlen),
+                     dsts=[(0, q, h, False), (h, fk, h, True), (2 * h, fv, h, True), (3 * h, R, nr, False)])
+            return q, fk, fv, R
+
+        ref = run(E, "cpu")
+        got = run(ops, DEV)
+        nat.device_check()
+        for name, a, b in zip("q k v R".split(), got, ref):
+            _close(f"fused qkvr {name} B={B} t={t} h={h}", a, b)
+        assert (got[1][:, :maxlen] == 0).all() and (got[2][:, :maxlen] == 0).all(), "memory rows must not be touched"

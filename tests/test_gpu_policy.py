@@ -233,3 +233,26 @@ def test_bench_workload_128x128_rows_match_oracle():
             e = rel_err(pd[k][b:b + 1].cpu(), pd_o[k])
             print(f"bench workload row {b} {k}: max rel err {e:.4g}")
             assert e < RTOL_BF16, (b, k, e)
+
+
+def test_config_c2_1x_B64_T128_rows_match_oracle():
+    """BASELINE configs[1] at its full size (1x width, B=64, T=128 = 8192 frames, 4 CNN sub-chunks): rows in different sub-chunks are
+    followed by the CPU oracle; identical sequences in different sub-chunks give bit-identical outputs."""
+    kw = vpt_b200.policy_kwargs("1x")
+    pol, sd, cfg = make_policy(kw, pert=True, seed=5)
+    pol = pol.to(DEV)
+    B, T = 64, 128
+    g = torch.Generator().manual_seed(23)
+    img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, generator=g)
+    img[40] = img[3]
+    first = torch.zeros(B, T, dtype=torch.bool)
+    (pd, v, _), st = pol({"img": img.to(DEV)}, first.to(DEV), pol.initial_state(B))
+    nat.device_check()
+    assert torch.equal(pd["buttons"][40], pd["buttons"][3]) and torch.equal(pd["camera"][40], pd["camera"][3])
+    for b in (3, 61):
+        with torch.no_grad():
+            (pd_o, _, _), _ = O.agent_policy_forward(sd, cfg, img[b:b + 1], first[b:b + 1], O.initial_state(cfg, 1))
+        for k in pd_o:
+            e = rel_err(pd[k][b:b + 1].cpu(), pd_o[k])
+            print(f"C2 row {b} {k}: max rel err {e:.4g}")
+            assert e < RTOL_BF16, (b, k, e)

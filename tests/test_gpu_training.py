@@ -282,6 +282,32 @@ def test_bc_training_reduces_the_loss():
     assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.5, losses
 
 
+def test_graphed_weight_relayout_equals_eager():
+    """BCTrainer.refresh_weights: from the second optimizer step on the kernel-side weight re-layout is one CUDA-graph replay; the
+    training trajectory must be bit-identical to the eager re-layout."""
+    img, first, actions = _case(seed=2, B=2)
+    img, first = img.to(DEV), first.to(DEV)
+    actions = {k: v.to(DEV) for k, v in actions.items()}
+    finals = []
+    for graphed in (False, True):
+        pol, _, _ = make_policy(small_kwargs(), seed=4)
+        pol = pol.to(DEV)
+        tr = BCTrainer(pol)
+        tr.graph_relayout = graphed
+        opt = FlatAdamDP([p for n, p in pol.named_parameters() if not n.startswith("value_head")], lr=2e-4)
+        losses = []
+        for _ in range(5):
+            opt.zero_grad()
+            loss, _ = tr.loss_and_grad(img, first, pol.initial_state(2), actions)
+            opt.step()
+            losses.append(loss.item())
+        assert (tr._rl_graph is not None) == graphed
+        finals.append((losses, opt.flat_p.clone()))
+    nat.device_check()
+    assert finals[0][0] == finals[1][0], (finals[0][0], finals[1][0])
+    assert torch.equal(finals[0][1], finals[1][1])
+
+
 def test_bc_step_at_3x_width_shapes():
     """BASELINE configs[3] layer shapes (3x: 192/384/384 channels, hidsize 3072, 24 heads, 128-frame memory, 128x128 frames) on
     a short clip: every backward kernel runs at its production shape, gradients are finite and Adam steps lower the loss."""

@@ -9,7 +9,7 @@ l = nat.lib()
 g = torch.Generator().manual_seed(0)
 shapes = [(64, 128, 256, 2048, False), (32, 256, 256, 2048, False), (32, 256, 256, 2048, True), (16, 256, 256, 2048, True),
           (64, 128, 128, 2048, True)]
-variants = [("tma/frag-epi", 1, 1), ("r1-epilogue", 0x101, 3)]
+variants = [("tma-epi/2phase", 1, 1), ("r1-epi/frag", 0x101, 4)]
 for (HW, Cin, N, F_, res) in shapes:
     x = torch.zeros(F_, HW + 1, HW + 1, Cin, dtype=torch.bfloat16, device="cuda")
     x[:, :HW, :HW] = torch.randn(F_, HW, HW, Cin, device="cuda").to(torch.bfloat16)

@@ -53,6 +53,8 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("out_f32", C.c_int32), ("ld_out", C.c_int64),
         ("seg_len", C.c_int32), ("seg_stride", C.c_int64), ("seg_off", C.c_int64),
         ("stat_part", C.c_void_p), ("stat_mode", C.c_int32), ("cluster", C.c_int32),
+        ("ndst", C.c_int32), ("dst_n0", C.c_int32 * 4), ("dst_out", C.c_void_p * 4), ("dst_ld", C.c_int64 * 4), ("dst_f32", C.c_int32 * 4),
+        ("dst_remap", C.c_int32 * 4),
     ]
 
 

@@ -536,8 +536,12 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(p.a_box_rows <= 256, "vpt_conv3x3_zp: span does not fit the TMA box limit");
     p.a_stage_bytes = p.a_boxes * p.a_box_rows * 128;
     const uint32_t w_stage_bytes = 128 * kBlockK * 2;
-    // g_cz_swap: 1 = fragment epilogue (stmatrix + TMA store), 3 = the round-1 epilogue (A/B knob), 2 = debug (no epilogue work)
-    p.epi_mode = (g_cz_swap == 1 && ((uintptr_t)a->out & 127) == 0 && (!a->residual || ((uintptr_t)a->residual & 127) == 0)) ? 1 : 0;
+    // g_cz_swap: 1 = transposing two-phase epilogue (default: measured faster, see below), 4 = fragment epilogue (tcgen05.ld.16x256b ->
+    // stmatrix.trans -> TMA store; needs maps of >= 256 rows per frame so that a tile touches at most two frames), 2 = debug (no epilogue).
+    // Round-2 A/B on B200 (tools/conv_bench.py, 128->128 @64x64, 2048 frames, residual): two-phase 2.144 ms (1154 TFLOP/s), fragment
+    // 2.207 ms (1121): the fragment path moves the same bytes through shared memory (the residual now arrives there too) and pays ~3x
+    // the instructions for the per-value border-class fold, so it stays an experiment.
+    p.epi_mode = (g_cz_swap == 4 && p.FS >= kCtPix && ((uintptr_t)a->out & 127) == 0 && (!a->residual || ((uintptr_t)a->residual & 127) == 0)) ? 1 : 0;
     const size_t bars_bytes = (4 + 2 * kCzMaxBStages + 4 + 4) * 8 + 16;
     const size_t tail = p.epi_mode == 1 ? 65536 + bars_bytes + 2 * 2 * 128 * 16 + 64
                                         : bars_bytes + 2 * 64 * kCtPitch * 4 + 2 * 64 * 16 + 64;
@@ -637,7 +641,7 @@ extern "C" int vpt_set_conv_swap_mode(int32_t on) {
 /* Statistics plumbing of the fragment-epilogue kernel (Cout == 128): number of floats of its partial buffer ([tiles][8 warps][2 frame
  * slots] float2), 0 when another kernel / epilogue handles this shape (then vpt_conv_zp_stat_parts + vpt_stats_finalize apply). */
 extern "C" int64_t vpt_conv_zp_t_stat_floats(int32_t F, int32_t H, int32_t W, int32_t Cout) {
-    if (Cout != 128 || vpt::g_cz_swap != 1) return 0;
+    if (Cout != 128 || vpt::g_cz_swap != 4 || (H + 1) * (W + 1) < vpt::kCtPix) return 0;
     const long long Q = (long long)F * (H + 1) * (W + 1);
     return ((Q + vpt::kCtPix - 1) / vpt::kCtPix) * 8 * 2 * 2;
 }

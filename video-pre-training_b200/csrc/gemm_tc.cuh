@@ -44,6 +44,13 @@ struct GemmParams {
     long long seg_stride, seg_off;
     float* stat_part;
     int stat_mode;
+    // column segments with their own destination (fused projections); ndst == 0: the single destination above
+    int ndst;
+    int dst_n0[4];
+    void* dst_out[4];
+    long long dst_ld[4];
+    int dst_f32[4];
+    int dst_remap[4];
     // weight-gradient mode (kWgrad): out[split][m][tap*N + n] = sum over this split's K rows of A[k][m] * B[k + tap_shift[tap]][n]
     // (both operands MN-major: A is [K rows][M], B is [K rows][N] in memory)
     int ntaps, k_splits, k_iters_split;
@@ -215,7 +222,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c_end = chalf == 0 ? (nchunks + 1) >> 1 : nchunks;
         const int P = p.num_n_tiles * 2;
         const bool tab_vec = (p.conv == 0) || ((p.N & 3) == 0);
-        const bool out_vec = ((p.ld_out & 7) == 0);
         const bool res_vec = ((p.ld_res & 7) == 0);
         int local = 0;
         bool ok = true;
@@ -246,8 +252,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             const float* s1row = p.S1 ? p.S1 + (size_t)cls * p.N : nullptr;
             const float* s2row = p.S2 ? p.S2 + (size_t)cls * p.N : nullptr;
+            // destination of this tile's columns (uniform per tile: segments start on tile boundaries)
+            void* d_out = p.out;
+            long long d_ld = p.ld_out;
+            int d_f32 = p.out_f32, d_col0 = 0;
+            bool d_remap = p.seg_len > 0;
+            if (p.ndst > 0) {
+                int sg = 0;
+                for (int i = 1; i < p.ndst; ++i)
+                    if (n0 >= p.dst_n0[i]) sg = i;
+                d_out = p.dst_out[sg]; d_ld = p.dst_ld[sg]; d_f32 = p.dst_f32[sg]; d_col0 = p.dst_n0[sg];
+                d_remap = d_remap && p.dst_remap[sg] != 0;
+            }
+            const bool d_vec = d_f32 ? ((d_ld & 3) == 0) : ((d_ld & 7) == 0);
             long long orow = m;
-            if (p.seg_len > 0) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
+            if (d_remap) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
             float st_s = 0.f, st_ss = 0.f;
 
             if (!(ok = mbar_wait(&tmem_full_bar[as], aphase, 0x400u))) break;
@@ -329,10 +348,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
                 }
                 // ---- store (+ statistics of the stored values)
-                if (p.out_f32) {
-                    float* op = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ld_out + nb;
+                if (d_f32) {
+                    float* op = reinterpret_cast<float*>(d_out) + (size_t)orow * d_ld + (nb - d_col0);
                     if (kWgrad) op += (size_t)split * p.split_stride + (size_t)tap * p.N;
-                    if (full && (p.ld_out & 3) == 0) {
+                    if (full && d_vec) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
                             reinterpret_cast<float4*>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -350,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                     }
                 } else {
-                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ld_out + nb;
+                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d_out) + (size_t)orow * d_ld + (nb - d_col0);
                     uint32_t pk[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
@@ -362,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (2 * j + 1 < lim) { st_s += hi; st_ss = fmaf(hi, hi, st_ss); }
                         }
                     }
-                    if (full && out_vec) {
+                    if (full && d_vec) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             reinterpret_cast<uint4*>(op)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -496,7 +515,7 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     VPT_CHECK(a->mr == nullptr || a->rows_per_group > 0, "vpt_gemm_bf16: rows_per_group must be > 0 with mr");
     VPT_CHECK(a->stat_part == nullptr || a->stat_mode == 1 || a->stat_mode == 2, "vpt_gemm_bf16: bad stat_mode %d", a->stat_mode);
     VPT_CHECK(!(a->mr && !a->S1), "vpt_gemm_bf16: mr given without S1");
-    if (g_small_m_enabled) {  // rollout path: a handful of rows -> weight-streaming kernel (csrc/gemv_small.cuh)
+    if (g_small_m_enabled && a->ndst == 0) {  // rollout path: a handful of rows -> weight-streaming kernel (csrc/gemv_small.cuh)
         const int r = try_launch_gemv_small_fwd(a, stream);
         if (r <= 0) return r;
     }
@@ -504,6 +523,14 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     memset(&p, 0, sizeof(p));
     p.M = a->M; p.N = a->N; p.K = a->K;
     choose_block_n(a->N, &p.block_n, &p.num_n_tiles);
+    if (a->ndst > 0) {  // segments start on N-tile boundaries: the largest tile width that divides every segment start
+        int bn = 256;
+        for (int i = 1; i < a->ndst && i < 4; ++i)
+            while (bn > 16 && a->dst_n0[i] % bn != 0) bn >>= 1;
+        if (bn > (a->N + 15) / 16 * 16) bn = (a->N + 15) / 16 * 16;
+        p.block_n = bn;
+        p.num_n_tiles = (a->N + bn - 1) / bn;
+    }
     p.num_m_tiles = (a->M + kBlockM - 1) / kBlockM;
     p.conv = a->conv;
     CUtensorMap tmA, tmB;
@@ -568,6 +595,14 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     p.seg_len = a->seg_len; p.seg_stride = a->seg_stride; p.seg_off = a->seg_off;
     p.stat_part = a->stat_part; p.stat_mode = a->stat_mode;
     VPT_CHECK(!(a->mr && !a->S1), "vpt_gemm_bf16: mr given without S1");
+    VPT_CHECK(a->ndst >= 0 && a->ndst <= 4, "vpt_gemm_bf16: ndst=%d not in 0..4", a->ndst);
+    p.ndst = a->ndst;
+    for (int i = 0; i < a->ndst; ++i) {
+        VPT_CHECK(a->dst_out[i] != nullptr && a->dst_n0[i] % p.block_n == 0 && (i == 0 ? a->dst_n0[0] == 0 : a->dst_n0[i] > a->dst_n0[i - 1]),
+                  "vpt_gemm_bf16: destination segment %d must start on an N-tile boundary (n0=%d, tile %d) in ascending order", i, a->dst_n0[i], p.block_n);
+        p.dst_n0[i] = a->dst_n0[i]; p.dst_out[i] = a->dst_out[i]; p.dst_ld[i] = a->dst_ld[i]; p.dst_f32[i] = a->dst_f32[i]; p.dst_remap[i] = a->dst_remap[i];
+    }
+    VPT_CHECK(!(a->ndst > 0 && a->stat_part), "vpt_gemm_bf16: statistics partials are not supported with destination segments");
 
     static bool attr_set = false;
     if (!attr_set) {

@@ -38,8 +38,9 @@ def _cuda(*ts):
 
 
 def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, S2=None, relu=0, out_scale=1.0,
-         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0, cluster=0):
-    """out = epilogue(A @ Bw^T); see struct vpt_gemm_args."""
+         residual=None, ld_out=None, seg=None, stat_part=None, stat_mode=0, cluster=0, dsts=None):
+    """out = epilogue(A @ Bw^T); see struct vpt_gemm_args.  dsts: up to 4 column segments [(n0, tensor, ld, remap)] with their own
+    destination buffer (then `out` is only used for its device / may be the first segment's tensor)."""
     _cuda(A, Bw, out)
     a = nat.GemmArgs()
     a.A, a.B, a.M, a.N, a.K = _p(A), _p(Bw), M, N, K
@@ -54,6 +55,11 @@ def gemm(A, Bw, out, M, N, K, *, conv=None, mr=None, rows_per_group=1, S1=None, 
     if seg is not None:
         a.seg_len, a.seg_stride, a.seg_off = seg
     a.stat_part, a.stat_mode, a.cluster = _p(stat_part), stat_mode, cluster
+    if dsts:
+        a.ndst = len(dsts)
+        for i, (n0, t, ld, remap) in enumerate(dsts):
+            _cuda(t)
+            a.dst_n0[i], a.dst_out[i], a.dst_ld[i], a.dst_f32[i], a.dst_remap[i] = n0, _p(t), ld, int(t.dtype == F32), int(remap)
     prof = GEMM_PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -296,6 +296,13 @@ class _Prepared:
             L["k"] = _fold_linear(g(f"{o}.k_layer.weight"))
             L["v"] = _fold_linear(g(f"{o}.v_layer.weight"))
             L["r"] = _fold_linear(g(f"{o}.r_layer.weight"), bias=g(f"{o}.r_layer.bias"))
+            # fused projection (lib/xf.py:334-365: Q(+bias) | K | V | R(+bias) of the same x_hat): one GEMM over the concatenated weight with
+            # four column segments, each with its own destination (csrc/gemm_tc.cuh, vpt_gemm_args.dst_*)
+            causal = cfg.mask_style == "clipped_causal"
+            ws = [g(f"{o}.q_layer.weight"), g(f"{o}.k_layer.weight"), g(f"{o}.v_layer.weight")] + ([g(f"{o}.r_layer.weight")] if causal else [])
+            zb = torch.zeros_like(g(f"{o}.q_layer.bias"))
+            bs = [g(f"{o}.q_layer.bias"), zb, zb] + ([g(f"{o}.r_layer.bias")] if causal else [])
+            L["qkvr"] = _fold_linear(torch.cat(ws, 0), bias=torch.cat(bs, 0))
             L["b_nd"] = g(f"{o}.b_nd").float().contiguous()
             L["proj"] = _fold_linear(g(f"{o}.proj_layer.weight"), bias=g(f"{o}.proj_layer.bias"))
             L["mlp0"] = _fold_linear(g(f"{b}.mlp0.layer.weight"), g(f"{b}.mlp0.norm.weight"), g(f"{b}.mlp0.norm.bias"))
@@ -446,12 +453,22 @@ class MinecraftPolicy(nn.Module):
                 raise AssertionError(f"KV memory shape {tuple(mem_k.shape)} != {(B, maxlen, h)}")
             ops.copy_rows(mem_k, 0, full_k, 0, maxlen)  # lib/xf.py:378-379  full = cat(prev, new)
             ops.copy_rows(mem_v, 0, full_v, 0, maxlen)
-        q, _ = self._linear(xhat, L["q"], h)
-        self._linear(xhat, L["k"], h, out=full_k, seg=(t, T, maxlen), ld_out=h)
-        self._linear(xhat, L["v"], h, out=full_v, seg=(t, T, maxlen), ld_out=h)
         R = None
-        if causal:
-            R, _ = self._linear(xhat, L["r"], NBASIS * heads, out_dtype=F32)
+        if B * t > 8 and h % 256 == 0:
+            # Q | K | V | R as ONE GEMM: K / V land in the rows of `full` after the memory (row remap), R in fp32
+            q = torch.empty((B * t, h), dtype=BF16, device=x.device)
+            dsts = [(0, q, h, False), (h, full_k, h, True), (2 * h, full_v, h, True)]
+            if causal:
+                R = torch.empty((B * t, NBASIS * heads), dtype=F32, device=x.device)
+                dsts.append((3 * h, R, NBASIS * heads, False))
+            Wc, _, bc = L["qkvr"]
+            ops.gemm(xhat, Wc, q, B * t, Wc.shape[0], h, S2=bc, seg=(t, T, maxlen), dsts=dsts)
+        else:  # a handful of rows (rollout): four weight-streaming launches (csrc/gemv_small.cuh)
+            q, _ = self._linear(xhat, L["q"], h)
+            self._linear(xhat, L["k"], h, out=full_k, seg=(t, T, maxlen), ld_out=h)
+            self._linear(xhat, L["v"], h, out=full_v, seg=(t, T, maxlen), ld_out=h)
+            if causal:
+                R, _ = self._linear(xhat, L["r"], NBASIS * heads, out_dtype=F32)
         smask_u8 = state_mask.contiguous().view(torch.uint8) if state_mask is not None else None
         a = ops.attention(q, full_k, full_v, R, L["b_nd"], first_u8, smask_u8, B, t, maxlen, heads, causal=causal)
         # new state (lib/xf.py:380-381: last `maxlen` rows of full; lib/masked_attention.py:86-92)
@@ -624,21 +641,27 @@ class _PolicyBase(nn.Module):
             self._hpprep_fp = fp
         return self._hpprep
 
+    def _heads_fp(self):
+        return tuple((p.data_ptr(), p._version) for n, p in self.named_parameters() if not n.startswith("net."))
+
+    def _build_heads_prepared(self):
+        ws, bs, cols, c0 = [], [], OrderedDict(), 0
+        for name, (shape, n) in self.head_specs.items():
+            lin = getattr(self.pi_head, name).linear_layer
+            ws.append(lin.weight.detach())
+            bs.append(lin.bias.detach())
+            cols[name] = (c0, lin.weight.shape[0])
+            c0 += lin.weight.shape[0]
+        hp = dict(pi=_fold_linear(torch.cat(ws, 0), bias=torch.cat(bs, 0)), cols=cols, ntot=c0)
+        if self.has_value_head:
+            hp["v"] = _fold_linear(self.value_head.linear.weight.detach(), bias=self.value_head.linear.bias.detach())
+        return hp
+
     def _heads_prepared(self):
-        params = [p for n, p in self.named_parameters() if not n.startswith("net.")]
-        fp = tuple((p.data_ptr(), p._version) for p in params)
+        fp = self._heads_fp()
         if self._hprep is None or fp != self._hprep_fp:
             with torch.no_grad():
-                ws, bs, cols, c0 = [], [], OrderedDict(), 0
-                for name, (shape, n) in self.head_specs.items():
-                    lin = getattr(self.pi_head, name).linear_layer
-                    ws.append(lin.weight.detach())
-                    bs.append(lin.bias.detach())
-                    cols[name] = (c0, lin.weight.shape[0])
-                    c0 += lin.weight.shape[0]
-                self._hprep = dict(pi=_fold_linear(torch.cat(ws, 0), bias=torch.cat(bs, 0)), cols=cols, ntot=c0)
-                if self.has_value_head:
-                    self._hprep["v"] = _fold_linear(self.value_head.linear.weight.detach(), bias=self.value_head.linear.bias.detach())
+                self._hprep = self._build_heads_prepared()
             self._hprep_fp = fp
         return self._hprep
 

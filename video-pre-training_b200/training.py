@@ -60,6 +60,9 @@ class BCTrainer:
         self.debug_grads = None  # set to a dict to capture d loss / d activation under the forward's tap names (tests)
         self.keep_tape = False   # tests: keep the last forward's tape in `self.last_tape` (tests/forced_replica.py)
         self.last_tape = None
+        self.graph_relayout = True  # re-layout of the kernel-side weights after an optimizer step as one CUDA graph replay
+        self._rl_graph = None
+        self._rl_seen = 0
 
     def _dbg(self, name, g):
         if self.debug_grads is not None:
@@ -67,10 +70,50 @@ class BCTrainer:
 
     # -- backward-side weight layouts (re-made whenever a parameter changes, like policy._Prepared) -------------------
     def _weights(self):
-        pol, net = self.policy, self.policy.net
-        fp = tuple((p.data_ptr(), p._version) for p in pol.parameters())
+        fp = tuple((p.data_ptr(), p._version) for p in self.policy.parameters())
         if self._wprep is not None and fp == self._wprep_fp:
             return self._wprep
+        with torch.no_grad():
+            self._wprep = self._build_weights()
+        self._wprep_fp = fp
+        return self._wprep
+
+    def refresh_weights(self):
+        """Re-layout of every kernel-side weight copy (forward folds of policy._Prepared + the heads, backward transposes of
+        `_build_weights`) after an optimizer step.  Eagerly this is ~500 small torch launches (12 ms at 3x width, profiles/bc_step_r1.md);
+        the parameters live at fixed addresses (FlatAdamDP's flat bucket), so from the second refresh on the whole re-layout is ONE captured
+        CUDA graph replay writing the same kernel-layout tensors in place.  Called by `loss_and_grad`; a no-op when nothing changed."""
+        pol, net = self.policy, self.policy.net
+        from .policy import _Prepared, _fingerprint
+        fp_net, fp_heads = _fingerprint(net), pol._heads_fp()
+        fp_all = tuple((p.data_ptr(), p._version) for p in pol.parameters())
+        if net._prep is not None and net._prep_fp == fp_net and pol._hprep is not None and pol._hprep_fp == fp_heads and self._wprep is not None \
+                and self._wprep_fp == fp_all:
+            return
+        ptrs = tuple(p.data_ptr() for p in pol.parameters())
+        if not self.graph_relayout or not all(p.is_cuda for p in pol.parameters()):
+            return  # the lazy eager paths (prepared() / _heads_prepared() / _weights()) rebuild on use
+        if self._rl_graph is not None and self._rl_graph[0] != ptrs:
+            self._rl_graph = None  # the parameters moved (e.g. .to(), a new optimizer bucket): capture again
+        if self._rl_graph is None:
+            self._rl_seen += 1
+            if self._rl_seen < 2:
+                return  # first change: eager (also warms up every lazily initialised helper before capture)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.no_grad(), torch.cuda.graph(g):
+                prep = _Prepared(net.cfg, dict(net.named_parameters()))
+                hprep = pol._build_heads_prepared()
+                wprep = self._build_weights()
+            self._rl_graph = (ptrs, g, prep, hprep, wprep)
+        _, g, prep, hprep, wprep = self._rl_graph
+        g.replay()
+        net._prep, net._prep_fp = prep, fp_net
+        pol._hprep, pol._hprep_fp = hprep, fp_heads
+        self._wprep, self._wprep_fp = wprep, fp_all
+
+    def _build_weights(self):
+        pol, net = self.policy, self.policy.net
         cfg = net.cfg
         P = dict(net.named_parameters())
         w = dict(stacks=[], layers=[])
@@ -103,12 +146,10 @@ class BCTrainer:
             w["layers"].append(dict(qkvr_t=_tr(cat, self.kcat), proj_t=_tr(P[f"{o}.proj_layer.weight"]), mlp0_t=_tr(P[f"{b}.mlp0.layer.weight"]),
                                     mlp1_t=_tr(P[f"{b}.mlp1.layer.weight"])))
         w["last_t"] = _tr(P["lastlayer.layer.weight"])
-        hp = pol._heads_prepared()
-        self.ntot = hp["ntot"]
+        self.ntot = sum(getattr(pol.pi_head, name).linear_layer.weight.shape[0] for name in pol.head_specs)
         self.ld_logits = (self.ntot + 7) // 8 * 8
         cat = torch.cat([getattr(pol.pi_head, name).linear_layer.weight for name in pol.head_specs], 0)
         w["heads_t"] = _tr(cat, self.ld_logits)
-        self._wprep, self._wprep_fp = w, fp
         return w
 
     # -- generic pieces -------------------------------------------------------------------------------------------------
@@ -176,6 +217,7 @@ class BCTrainer:
         backward, most of the step's time, is still to come): the hook for `FlatAdamDP.reduce_async`."""
         pol, net = self.policy, self.policy.net
         cfg = net.cfg
+        self.refresh_weights()
         wts = self._weights()
         P = dict(net.named_parameters())
         B, t = img.shape[:2]
