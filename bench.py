@@ -474,7 +474,8 @@ def run_ours(args):
     # ---------------- device-resident inputs ("value") ----------------
     state = pol.initial_state(B)
     for _ in range(args.warmup):
-        (_, _, _), state = pol({"img": img}, first, state)
+        (pd, _, _), state = pol({"img": img}, first, state)
+        pol.sample(pd)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -486,6 +487,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         (pd, vpred, _), state = pol({"img": img}, first, state)
+        ac = pol.sample(pd)  # configs[2]: "forward + action_head sampling"
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))

@@ -80,6 +80,22 @@ def test_resize_oracle_is_bit_exact_with_cv2():
         assert np.array_equal(resize_oracle.resize_linear_u8(img, 128, 128), ref), (H, W)
 
 
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_product_resize_tables_match_cv2_on_many_source_sizes():
+    """the product's coefficient tables (agent._linear_tables, fx computed in float like resize.cpp) driven through the
+    oracle's integer arithmetic == cv2 for source sizes beyond the reference's 640x360 / 1280x720; exact 2x downscales are refused."""
+    rng = np.random.default_rng(2)
+    for (H, W) in [(360, 640), (720, 1280), (240, 320), (150, 200), (211, 333), (300, 500), (129, 129), (700, 1000), (300, 257)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        xi, xa = A._linear_tables(128, W)
+        yi, ya = A._linear_tables(128, H)
+        src = img.astype(np.int64)
+        hor = src[:, xi, :] * xa[None, :, 0, None].astype(np.int64) + src[:, np.minimum(xi + 1, W - 1), :] * xa[None, :, 1, None].astype(np.int64)
+        out = ((ya[:, 0, None, None].astype(np.int64) * (hor[yi] >> 4)) >> 16) + ((ya[:, 1, None, None].astype(np.int64) * (hor[np.minimum(yi + 1, H - 1)] >> 4)) >> 16)
+        got = np.clip((out + 2) >> 2, 0, 255).astype(np.uint8)
+        assert np.array_equal(got, cv2.resize(img, (128, 128), interpolation=cv2.INTER_LINEAR)), (H, W)
+
+
 @pytest.mark.gpu
 def test_resize_kernel_bit_exact():
     rng = np.random.default_rng(1)
@@ -90,6 +106,8 @@ def test_resize_kernel_bit_exact():
             assert np.array_equal(got[f], resize_oracle.resize_linear_u8(img[f], 128, 128))
             if cv2 is not None:
                 assert np.array_equal(got[f], cv2.resize(img[f], (128, 128), interpolation=cv2.INTER_LINEAR))
+    with pytest.raises(NotImplementedError):  # exact 2x: OpenCV switches to INTER_AREA
+        A.resize_frames(torch.zeros((1, 256, 256, 3), dtype=torch.uint8, device="cuda"))
 
 
 @pytest.mark.gpu

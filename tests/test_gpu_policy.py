@@ -11,6 +11,10 @@ from video_pre_training_b200 import _native as nat
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 RTOL_BF16 = 1e-2
+# side outputs (value head, KV state): bf16-path bounds tightened in round 2 from 0.1 / 5e-2 (measured values are printed by the tests)
+# (vpred: the head is a 1-wide Linear on the bf16 latent, |v| ~ 1; KV state: the bf16-rounded K / V projections)
+VPRED_ATOL = 5e-2
+KV_L2 = 3e-2
 
 
 def _check(res, tag):
@@ -20,10 +24,13 @@ def _check(res, tag):
             assert got.shape == r["pd_o"][k].shape and torch.isfinite(got).all()
             e = rel_err(got, r["pd_o"][k])
             assert e < RTOL_BF16, f"{tag} chunk {ci} head {k}: max rel err {e:.4g} (l2 {l2_err(got, r['pd_o'][k]):.3g})"
-        assert (r["v"].cpu() - r["v_o"]).abs().max() < 0.1
+        ve = (r["v"].cpu() - r["v_o"]).abs().max().item()
+        kerr = max(max(l2_err(k_.cpu(), ko), l2_err(v_.cpu(), vo)) for (m, (k_, v_)), (mo, (ko, vo)) in zip(r["st"], r["st_o"]))
+        print(f"{tag} chunk {ci}: vpred max abs err {ve:.3e} (|v| max {r['v_o'].abs().max().item():.3f}); worst KV-state rel-L2 {kerr:.3e}")
+        assert ve < VPRED_ATOL
         for (m, (k_, v_)), (mo, (ko, vo)) in zip(r["st"], r["st_o"]):
             assert torch.equal(m.cpu(), mo)
-            assert l2_err(k_.cpu(), ko) < 5e-2 and l2_err(v_.cpu(), vo) < 5e-2
+        assert kerr < KV_L2
 
 
 def _layer_report(r):
@@ -114,6 +121,7 @@ def test_chunk_invariance_and_reset_on_gpu():
             (pd, _, _), st = pol({"img": img[:, t0:t0 + cs]}, torch.zeros(B, cs, dtype=torch.bool, device=DEV), st)
             acc.append(pd["camera"])
         outs.append(torch.cat(acc, 1))
+    print(f"chunk invariance: max abs diff of the camera log-probs {(outs[0] - outs[1]).abs().max().item():.3e}")
     assert (outs[0] - outs[1]).abs().max() < 3e-2
     first = torch.zeros(B, 8, dtype=torch.bool, device=DEV)
     first[:, 0] = True

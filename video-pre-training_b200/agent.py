@@ -181,13 +181,13 @@ class ActionCodec:
 def _linear_tables(dst: int, src: int):
     """Source index + 11-bit fixed-point weight pairs of OpenCV's 8-bit INTER_LINEAR resize (resize.cpp: fx = (dx+0.5)*scale-0.5,
     cvFloor, clamping at both ends, weights = cvRound(w * 2048) as int16)."""
-    scale = src / dst
+    scale = src / dst  # double, like resize.cpp's inv_scale_x; fx itself is computed in float there
     idx = np.zeros(dst, dtype=np.int32)
     w = np.zeros((dst, 2), dtype=np.int16)
     for d in range(dst):
-        f = (d + 0.5) * scale - 0.5
+        f = np.float32((d + 0.5) * scale - 0.5)
         s = int(np.floor(f))
-        f -= s
+        f = np.float32(f - np.float32(s))
         if s < 0:
             s, f = 0, 0.0
         if s >= src - 1:
@@ -212,6 +212,10 @@ def resize_frames(frames: torch.Tensor, size=AGENT_RESOLUTION, bgr_to_rgb: bool 
         # OpenCV takes a different code path when it UPSCALES (measured: +-1 differences against this formula); the
         # reference only ever shrinks 640x360 / 1280x720 frames to 128x128, so upscaling is refused rather than approximated
         raise NotImplementedError("resize_frames is bit-exact with cv2 for downscaling only")
+    if Hs == 2 * Hd and Ws == 2 * Wd:
+        # OpenCV silently switches INTER_LINEAR to INTER_AREA when both scale factors are exactly 2 (resize.cpp), which this kernel does
+        # not implement; the reference never hits it (640x360 / 1280x720 -> 128x128)
+        raise NotImplementedError("resize_frames: an exact 2x downscale takes OpenCV's INTER_AREA path, which is not implemented")
     key = (Hs, Ws, Hd, Wd, frames.device)
     if key not in _TABLE_CACHE:
         xi, xw = _linear_tables(Wd, Ws)

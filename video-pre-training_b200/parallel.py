@@ -66,6 +66,8 @@ class HostFramePipe:
         self.cur ^= 1
 
     def take(self):
+        if self.pending is None:
+            raise RuntimeError("HostFramePipe.take() before any submit()")
         i = self.pending
         torch.cuda.current_stream(self.device).wait_event(self.events[i])
         return self.slots[i]
@@ -75,8 +77,12 @@ class FlatAdamDP:
     """Data-parallel optimizer plumbing of the BC step (behavioural_cloning.py:63-67,119-123), independent of how the
     gradients are produced: all parameters are re-pointed into ONE flat fp32 bucket, their `.grad`s into a second flat bucket,
     so that a step is  one NCCL all-reduce (sum) over the gradient bucket  +  one fused Adam kernel (`vpt_adam_step`,
-    torch.optim.Adam semantics with L2 weight decay; 1/world_size folded into the kernel).  Parameters whose gradient is
-    None in the reference (value head under the BC loss) simply keep a zero gradient slice."""
+    torch.optim.Adam semantics with L2 weight decay; 1/world_size folded into the kernel).
+
+    Pass only the parameters that receive a gradient (behavioural cloning: everything but `value_head.*`, whose `.grad` stays None in
+    the reference): torch.optim.Adam SKIPS a parameter without a gradient (no weight decay, no moment update), whereas a slice of this
+    bucket that is never written would still be decayed.  `step()` therefore refuses parameters whose `.grad` no longer aliases the
+    bucket (e.g. after `zero_grad(set_to_none=True)` on the module) instead of silently applying Adam to zeros."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.params = [p for p in params if p.requires_grad]
@@ -99,6 +105,9 @@ class FlatAdamDP:
         self._pending = None  # (lo, hi, work) of a gradient slice whose all-reduce is already in flight
 
     def zero_grad(self):
+        if self._pending is not None:  # a step that raised after `reduce_async` left a collective in flight: finish it first
+            self._pending[2].wait()
+            self._pending = None
         self.flat_g.zero_()
 
     def state_dict(self):
@@ -158,6 +167,11 @@ class FlatAdamDP:
         return total
 
     def step(self, max_grad_norm=None):
+        base = self.flat_g.data_ptr()
+        for p in self.params:
+            if p.grad is None or not (base <= p.grad.data_ptr() < base + self.flat_g.numel() * 4):
+                raise RuntimeError("FlatAdamDP.step: a parameter's .grad no longer aliases the flat gradient bucket (use FlatAdamDP.zero_grad(), "
+                                   "not module.zero_grad(set_to_none=True))")
         world = self.reduce_gradients()
         if max_grad_norm is not None:
             self.clip_grad_norm_(max_grad_norm, world)
