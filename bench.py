@@ -29,8 +29,8 @@ import torch  # noqa: E402
 
 METRIC = "frames/sec MinecraftPolicy fwd, 128x128x3 BxT=128x128"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (conv3x3_zp_kernel, 128->128 @64x64, 2048 frames)
-# from the committed `ncu --set full` capture (profiles/conv_zp_r1.md); null until measured
-TRAFFIC_NCU = 2.274e9  # 1.146 GB read + 1.128 GB written (conv3x3_zp_kernel<pair>, 256->256 @32x32, 2048 frames; algorithmic 2.28 GB)
+# from the committed ncu capture (profiles/conv_zp_r2.md, profiles/kernels_r2.csv)
+TRAFFIC_NCU = 2.307e9  # 1.171 GB read + 1.136 GB written (conv3x3_zp_kernel<pair>, 256->256 @32x32, 2048 frames; algorithmic 2.28 GB; profiles/conv_zp_r2.md)
 
 
 def parse():

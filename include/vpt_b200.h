@@ -121,6 +121,15 @@ typedef struct vpt_conv_zp_args {
     const void* residual;     /* bf16 ZP [F][H+1][W+1][Cout] or NULL */
     void* out;                /* bf16 ZP [F][H+1][W+1][Cout] */
     float* stat_part;         /* NULL or float2 [F*(H+1)*(W+1)][vpt_conv_zp_stat_parts(Cout)] per-row partials */
+    /* Two-norm composition (the post-pool GroupNorm `n` of lib/impala_cnn.py:119 folded into its two consumers instead of running as a
+     * pass of its own; tables from vpt_norm2_fold):
+     *   Ef        [F][9][Cout] or NULL: per-FRAME additive fold table; out = rstd_f * acc + Ef[f][cls][c] (replaces -rstd*mean*S1 + S2; mr
+     *             then carries (0, rstd_f) per frame and S1 / S2 are ignored)
+     *   res_scale / res_shift [F][Cout] or NULL: the residual enters as res_scale[f][c] * residual + res_shift[f][c] (the residual
+     *             stream x0 = n(y1) recomputed from the un-normalised tensor y1) */
+    const float* Ef;
+    const float* res_scale;
+    const float* res_shift;
 } vpt_conv_zp_args;
 
 int vpt_conv3x3_zp(const vpt_conv_zp_args* args, void* stream);
@@ -205,7 +214,19 @@ int vpt_conv3d_stat_parts(int32_t H, int32_t W, int32_t C);
 /* max_pool2d(kernel 3, stride 2, pad 1) on a non-negative NHWC bf16 tensor (lib/impala_cnn.py:117).
  *   in [F][H][W][C] -> out [F][H/2][W/2][C]   (zp=1: both in the ZP layout, [F][H+1][W+1][C] -> [F][H/2+1][W/2+1][C])
  *   stat_part float2 [F][vpt_pool_stat_parts()] */
-int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp, void* stream);
+int vpt_maxpool3s2(const void* in, void* out, float* stat_part, float* chan_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp,
+                   void* stream);  /* chan_part: NULL or float2 [F][vpt_pool_stat_parts(H, W, C)][C] per-channel partials (needs C/8 | 256) */
+/* Two-norm composition: the post-pool GroupNorm `n` (lib/impala_cnn.py:119) is not run as a pass; its effect is folded into the two
+ * consumers of x0 = n(y1): block 0's conv0 (input y1, weights W*gamma0*gamma_n, per-frame table Ef) and conv1 (residual y1 with a
+ * per-frame affine).  From the per-channel (sum, sumsq) partials of y1 [F][NP][C] (vpt_firstconv_pool / vpt_maxpool3s2), gamma_n / beta_n
+ * and conv0's class tables Ta = sum W gamma0 beta_n, Tb = sum bf16(W gamma0 gamma_n), Tc = sum W gamma0, Td = sum W beta0 (each [9][Cout],
+ * summed over the taps inside the image for the border class and over Cin) this writes, per frame:
+ *   mrE [F][2] = (0, rstd0 * rstd1)        Ef [F][9][Cout] = rstd0 Ta - rstd0 rstd1 mu1 Tb - rstd0 mu0 Tc + Td
+ *   res_scale [F][C] = rstd1 gamma_n        res_shift [F][C] = beta_n - mu1 rstd1 gamma_n
+ * (mu1, rstd1: statistics of y1; mu0, rstd0: statistics of x0, obtained analytically from the per-channel sums). */
+int vpt_norm2_fold(const float* chan_part, int32_t NP, int32_t C, int64_t npix, const float* gamma_n, const float* beta_n, const float* Ta,
+                   const float* Tb, const float* Tc, const float* Td, int32_t Cout, float eps, float* mrE, float* Ef, float* res_scale,
+                   float* res_shift, int64_t F, void* stream);
 int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C);
 
 /* out[m][c] = (in[m][c] - mean_g) * rstd_g * gamma[c] + beta[c],  g = m / rows_per_group   (bf16 in, bf16 out)

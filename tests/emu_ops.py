@@ -117,7 +117,36 @@ def _frame_stats(x_interior):
     return _row_stats(x_interior.reshape(x_interior.shape[0], -1), 1)
 
 
-def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True, out=None):
+def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True, out=None, Ef=None, res_scale=None,
+               res_shift=None):
+    if Ef is not None or res_scale is not None:  # two-norm composition: per-frame fold table / affine residual
+        F_, Cin = x.shape[0], x.shape[3]
+        Cout = Wb.shape[0]
+        xi = from_zp(x).float().permute(0, 3, 1, 2)
+        acc = F.conv2d(xi, Wb.float().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)  # [F,H,W,Cout]
+        yy, xx = torch.arange(H)[:, None], torch.arange(W)[None, :]
+        cls = (torch.where(yy == 0, 0, torch.where(yy == H - 1, 2, 1)) * 3 + torch.where(xx == 0, 0, torch.where(xx == W - 1, 2, 1)))  # [H,W]
+        if Ef is not None:
+            v = mr[:, 1, None, None, None] * acc + Ef[:, cls]           # Ef [F,9,Cout] -> [F,H,W,Cout]
+        else:
+            s1 = S1[cls] if S1 is not None else 0.0
+            s2 = S2[cls] if S2 is not None else 0.0
+            v = mr[:, 1, None, None, None] * acc - (mr[:, 1] * mr[:, 0])[:, None, None, None] * s1 + s2 if mr is not None else acc + s2
+        if relu == 1:
+            v = v.relu()
+        if residual is not None:
+            r = from_zp(residual).float()
+            if res_scale is not None:
+                r = res_scale[:, None, None, :] * r + res_shift[:, None, None, :]
+            v = v + r
+        if relu == 2:
+            v = v.relu()
+        o = v.to(BF16)
+        res = to_zp(o)
+        if out is not None:
+            out.copy_(res)
+            res = out
+        return res, (_frame_stats(o) if want_stats else None)
     F_, Cin = x.shape[0], x.shape[3]
     Cout = Wb.shape[0]
     assert (x[:, -1] == 0).all() and (x[:, :, -1] == 0).all(), "ZP invariant violated on the conv input"
@@ -135,13 +164,20 @@ def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None,
     return res, (_frame_stats(o) if want_stats else None)
 
 
-def firstconv_pool(img, w, bias, C0, zp=True, out_f32=False):
+def _chan_parts(y):
+    """[F,H,W,C] -> per-channel (sum, sumsq) [F, 1, C, 2] (one partial)"""
+    yf = y.float()
+    return torch.stack([yf.sum((1, 2)), (yf * yf).sum((1, 2))], -1)[:, None]
+
+
+def firstconv_pool(img, w, bias, C0, zp=True, out_f32=False, want_chan=False):
     F_, H, W, _ = img.shape
     x = img.float().permute(0, 3, 1, 2)
     wt = w.reshape(C0, 3, 3, 3).permute(0, 3, 1, 2)  # [C0][ky][kx][c] -> OIHW
     y = F.relu(F.conv2d(x, wt, bias, padding=1))
     y = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(F32 if out_f32 else BF16)
-    return (to_zp(y) if zp else y), _frame_stats(y)
+    r = ((to_zp(y) if zp else y), _frame_stats(y))
+    return r + (_chan_parts(y),) if want_chan else r
 
 
 def conv3d_t5(img, w, bias, C, out_f32=False):
@@ -209,10 +245,30 @@ def attention_f32(q, full_k, full_v, R, b_nd, first_u8, smask_u8, B, t, maxlen, 
     return (w @ v).permute(0, 2, 1, 3).reshape(B * t, h)
 
 
-def maxpool3s2(x, zp=True):
+def maxpool3s2(x, zp=True, want_chan=False):
     xi = from_zp(x) if zp else x
     y = F.max_pool2d(xi.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous().to(BF16)
-    return (to_zp(y) if zp else y), _frame_stats(y)
+    r = ((to_zp(y) if zp else y), _frame_stats(y))
+    return r + (_chan_parts(y),) if want_chan else r
+
+
+def norm2_fold(chan_part, npix, gamma_n, beta_n, tabs):
+    Ta, Tb, Tc, Td = [t.double() for t in tabs]
+    cp = chan_part.double().sum(1)                      # [F, C, 2]
+    S, Q = cp[..., 0], cp[..., 1]
+    Cc = S.shape[1]
+    cnt = float(npix) * Cc
+    mu1 = S.sum(1) / cnt
+    rstd1 = 1.0 / torch.sqrt((Q.sum(1) / cnt - mu1 * mu1).clamp(min=0) + 1e-5)
+    a = rstd1[:, None] * gamma_n.double()[None]
+    b = beta_n.double()[None] - mu1[:, None] * a
+    m0 = (a * S + npix * b).sum(1) / cnt
+    e0 = (a * a * Q + 2 * a * b * S + npix * b * b).sum(1) / cnt
+    rstd0 = 1.0 / torch.sqrt((e0 - m0 * m0).clamp(min=0) + 1e-5)
+    R = rstd0 * rstd1
+    Ef = rstd0[:, None, None] * Ta[None] - (R * mu1)[:, None, None] * Tb[None] - (rstd0 * m0)[:, None, None] * Tc[None] + Td[None]
+    mrE = torch.stack([torch.zeros_like(R), R], 1)
+    return mrE.float(), Ef.float(), a.float(), b.float()
 
 
 def affine_norm_zp(x, mr, gamma, beta):

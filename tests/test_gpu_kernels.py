@@ -341,3 +341,61 @@ def test_gemm_column_segments_fused_qkvr():
         for name, a, b in zip("q k v R".split(), got, ref):
             _close(f"fused qkvr {name} B={B} t={t} h={h}", a, b)
         assert (got[1][:, :maxlen] == 0).all() and (got[2][:, :maxlen] == 0).all(), "memory rows must not be touched"
+
+
+def test_two_norm_composition_kernels():
+    """vpt_norm2_fold + the Ef / res_scale modes of vpt_conv3x3_zp (every epilogue: SM pairs with TMA store, single CTA, operand-swapped)
+    + the per-channel partials of vpt_maxpool3s2 / vpt_firstconv_pool, each against the test-only emulation."""
+    g = torch.Generator().manual_seed(41)
+    # per-channel partials of the two pool producers
+    x = E.to_zp(_rand((3, 16, 16, 256), g).relu())
+    got, gmr, gch = ops.maxpool3s2(x.to(DEV), zp=True, want_chan=True)
+    ref, rmr, rch = E.maxpool3s2(x, zp=True, want_chan=True)
+    assert torch.equal(got.cpu(), ref)
+    _close("maxpool per-channel sums", gch.sum(1), rch.sum(1), rtol=1e-4, atol=1e-3)
+    img = torch.randint(0, 256, (2, 64, 64, 3), dtype=torch.uint8, generator=g)
+    w = torch.randn(128, 27, generator=g) / 255.0 * 0.3
+    b = torch.randn(128, generator=g) * 0.1
+    _, _, gch = ops.firstconv_pool(img.to(DEV), w.to(DEV), b.to(DEV), 128, zp=True, want_chan=True)
+    _, _, rch = E.firstconv_pool(img, w, b, 128, zp=True, want_chan=True)
+    _close("firstconv per-channel sums", gch.sum(1), rch.sum(1), rtol=2e-3, atol=5e-2)
+    # fold tables
+    F_, C, Cout = 5, 128, 128
+    chan = torch.rand(F_, 7, C, 2, generator=g) * 50 + 20
+    chan[..., 1] += chan[..., 0] ** 2 / 10
+    gn, bn = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    tabs = tuple(torch.randn(9, Cout, generator=g) for _ in range(4))
+    got = ops.norm2_fold(chan.to(DEV), 1024, gn.to(DEV), bn.to(DEV), tuple(t.to(DEV) for t in tabs))
+    ref = E.norm2_fold(chan, 1024, gn, bn, tabs)
+    for name, a, r in zip(("mrE", "Ef", "res_scale", "res_shift"), got, ref):
+        _close(f"norm2_fold {name}", a, r, rtol=1e-4, atol=1e-4)
+    # conv epilogues with a per-frame table and an affine residual
+    try:
+        for (H, W, Cin, Cout, F_, modes) in [(16, 16, 128, 256, 3, ((1, 1), (0x101, 1), (0, 1))), (32, 32, 128, 128, 2, ((1, 1), (1, 0))),
+                                             (8, 8, 64, 64, 5, ((1, 1),))]:
+            x = E.to_zp(_rand((F_, H, W, Cin), g))
+            Wb = _rand((Cout, 9 * Cin), g, (9 * Cin) ** -0.5)
+            mrE = torch.stack([torch.zeros(F_), torch.rand(F_, generator=g) + 0.5], 1)
+            Ef = torch.randn(F_, 9, Cout, generator=g)
+            res = E.to_zp(_rand((F_, H, W, Cout), g))
+            rs, rb = torch.randn(F_, Cout, generator=g), torch.randn(F_, Cout, generator=g)
+            mr = torch.stack([torch.randn(F_, generator=g) * 0.3, torch.rand(F_, generator=g) + 0.5], 1)
+            S1, S2 = torch.randn(9, Cout, generator=g), torch.randn(9, Cout, generator=g)
+            for pair, swap in modes:
+                nat.lib().vpt_set_conv_pair_mode(pair)
+                nat.lib().vpt_set_conv_swap_mode(swap)
+                got, gmr = ops.conv3x3_zp(x.to(DEV), Wb.to(DEV), H, W, mr=mrE.to(DEV), Ef=Ef.to(DEV), relu=1)
+                ref, rmr = E.conv3x3_zp(x, Wb, H, W, mr=mrE, Ef=Ef, relu=1)
+                nat.device_check()
+                _close(f"conv Ef pair={pair:#x} swap={swap} {Cin}->{Cout}@{H}", got, ref)
+                _close("conv Ef stats", gmr, rmr, rtol=2e-3, atol=2e-3, l2=1e-3)
+                got, gmr = ops.conv3x3_zp(x.to(DEV), Wb.to(DEV), H, W, mr=mr.to(DEV), S1=S1.to(DEV), S2=S2.to(DEV), relu=1, residual=res.to(DEV),
+                                          res_scale=rs.to(DEV), res_shift=rb.to(DEV))
+                ref, rmr = E.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, residual=res, res_scale=rs, res_shift=rb)
+                nat.device_check()
+                _close(f"conv affine residual pair={pair:#x} swap={swap} {Cin}->{Cout}@{H}", got, ref)
+                gc = got.cpu()
+                assert (gc[:, -1] == 0).all() and (gc[:, :, -1] == 0).all()
+    finally:
+        nat.lib().vpt_set_conv_pair_mode(1)
+        nat.lib().vpt_set_conv_swap_mode(1)

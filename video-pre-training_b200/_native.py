@@ -65,6 +65,7 @@ class ConvZpArgs(C.Structure):
         ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
         ("mr", C.c_void_p), ("S1", C.c_void_p), ("S2", C.c_void_p),
         ("relu", C.c_int32), ("residual", C.c_void_p), ("out", C.c_void_p), ("stat_part", C.c_void_p),
+        ("Ef", C.c_void_p), ("res_scale", C.c_void_p), ("res_shift", C.c_void_p),
     ]
 
 
@@ -98,7 +99,8 @@ SIGNATURES = {
     "vpt_codec_to_env": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P, _P, _P]),
     "vpt_codec_from_env": (_I, [_P, _P, _P, _I, _P, _L, _L, _P, _P]),
     "vpt_conv3d_stat_parts": (_I, [_I, _I, _I]),
-    "vpt_maxpool3s2": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vpt_maxpool3s2": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vpt_norm2_fold": (_I, [_P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _L, _P]),
     "vpt_pool_stat_parts": (_I, [_I, _I, _I]),
     "vpt_affine_norm": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "vpt_affine_norm_zp": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

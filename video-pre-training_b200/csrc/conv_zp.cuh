@@ -49,6 +49,9 @@ struct ConvZpParams {
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
     float* stat_part;  // [Q][2 * num_n_tiles] float2 or null
+    const float* Ef;         // [F][9][N] per-frame fold table (two-norm composition) or null
+    const float* res_scale;  // [F][N] or null: residual enters as res_scale * r + res_shift
+    const float* res_shift;
 };
 
 // kPair: two CTAs of a cluster (an SM pair) cooperate on a 256-row tile with tcgen05.mma.cta_group::2 -- each CTA stages
@@ -277,6 +280,12 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int cls = interior ? cy * 3 + cx : 0;
             const float* s1row = p.S1 ? p.S1 + (size_t)cls * p.N : nullptr;
             const float* s2row = p.S2 ? p.S2 + (size_t)cls * p.N : nullptr;
+            if (p.Ef) {  // per-frame fold table: out = ga * acc + Ef[f][cls][c]
+                s1row = nullptr;
+                s2row = p.Ef + ((size_t)(interior ? f : 0) * 9 + cls) * p.N;
+            }
+            const float* rarow = (p.res_scale && interior) ? p.res_scale + (size_t)f * p.N : nullptr;
+            const float* rbrow = (p.res_scale && interior) ? p.res_shift + (size_t)f * p.N : nullptr;
             float st_s = 0.f, st_ss = 0.f;
             if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x410u))) break;
             tc_fence_after();
@@ -313,10 +322,15 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int qq = 0; qq < 4; ++qq) {
                         uint4 rr;
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(brow + (((uint32_t)qq ^ swz) << 4)));
-                        v[8 * qq + 0] += bf16_lo(rr.x); v[8 * qq + 1] += bf16_hi(rr.x);
-                        v[8 * qq + 2] += bf16_lo(rr.y); v[8 * qq + 3] += bf16_hi(rr.y);
-                        v[8 * qq + 4] += bf16_lo(rr.z); v[8 * qq + 5] += bf16_hi(rr.z);
-                        v[8 * qq + 6] += bf16_lo(rr.w); v[8 * qq + 7] += bf16_hi(rr.w);
+                        float r8[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y), bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
+                        if (rarow) {  // residual stream recomputed from the un-normalised tensor: a[f][c] * r + b[f][c]
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(rarow + nb + 8 * qq)), a1 = __ldg(reinterpret_cast<const float4*>(rarow + nb + 8 * qq) + 1);
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(rbrow + nb + 8 * qq)), b1 = __ldg(reinterpret_cast<const float4*>(rbrow + nb + 8 * qq) + 1);
+                            r8[0] = fmaf(a0.x, r8[0], b0.x); r8[1] = fmaf(a0.y, r8[1], b0.y); r8[2] = fmaf(a0.z, r8[2], b0.z); r8[3] = fmaf(a0.w, r8[3], b0.w);
+                            r8[4] = fmaf(a1.x, r8[4], b1.x); r8[5] = fmaf(a1.y, r8[5], b1.y); r8[6] = fmaf(a1.z, r8[6], b1.z); r8[7] = fmaf(a1.w, r8[7], b1.w);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[8 * qq + e] += r8[e];
                     }
                 }
                 if (p.relu == 2) {
@@ -395,6 +409,12 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int cls = interior ? cy * 3 + cx : 0;
             const float* s1row = p.S1 ? p.S1 + (size_t)cls * p.N : nullptr;
             const float* s2row = p.S2 ? p.S2 + (size_t)cls * p.N : nullptr;
+            if (p.Ef) {  // per-frame fold table: out = ga * acc + Ef[f][cls][c]
+                s1row = nullptr;
+                s2row = p.Ef + ((size_t)(interior ? f : 0) * 9 + cls) * p.N;
+            }
+            const float* rarow = (p.res_scale && interior) ? p.res_scale + (size_t)f * p.N : nullptr;
+            const float* rbrow = (p.res_scale && interior) ? p.res_shift + (size_t)f * p.N : nullptr;
             float st_s = 0.f, st_ss = 0.f;
 
             if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x410u))) break;
@@ -445,7 +465,11 @@ conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 if (p.residual != nullptr) {
                     const __nv_bfloat16* rp = p.residual + (size_t)q * p.N + nb;
-                    if (full) {
+                    if (rarow) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < lim) v[j] += fmaf(__ldg(rarow + nb + j), __bfloat162float(rp[j]), __ldg(rbrow + nb + j));
+                    } else if (full) {
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq) {
                             uint4 rr = __ldg(reinterpret_cast<const uint4*>(rp) + qq);
@@ -589,11 +613,15 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
         int r = make_tmap_bf16(&tmB, a->w, 2, dims, strides, box);
         if (r) return r;
     }
-    VPT_CHECK(!(a->mr && !a->S1), "vpt_conv3x3_zp: mr given without S1");
+    VPT_CHECK(!(a->mr && !a->S1 && !a->Ef), "vpt_conv3x3_zp: mr given without S1 (or Ef)");
+    VPT_CHECK(!a->Ef || a->mr, "vpt_conv3x3_zp: Ef needs mr = (0, rstd) per frame");
+    VPT_CHECK(!a->res_scale == !a->res_shift && (!a->res_scale || a->residual) && (!a->res_scale || N % 8 == 0),
+              "vpt_conv3x3_zp: res_scale / res_shift come as a pair, with a residual, Cout %% 8 == 0");
     p.mr = a->mr; p.S1 = a->mr ? a->S1 : nullptr; p.S2 = a->S2; p.relu = a->relu;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     p.stat_part = a->stat_part;
+    p.Ef = a->Ef; p.res_scale = a->res_scale; p.res_shift = a->res_shift;
     p.dbg = g_cz_dbg;
 
     static bool attr_set = false;

@@ -31,6 +31,9 @@ struct ConvZpTParams {
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
     float* stat_part;  // epi_mode 0: [Q] float2 (complete row sums) or null; epi_mode 1: [num_tiles][8 warps][2 frame slots] float2
+    const float* Ef;         // [F][9][128] per-frame fold table (two-norm composition, see vpt_conv_zp_args) or null
+    const float* res_scale;  // [F][128] or null: the residual enters as res_scale * r + res_shift
+    const float* res_shift;
     int epi_mode;      // 1: fragment epilogue (tcgen05.ld.16x256b -> stmatrix.trans -> TMA store, TMA-prefetched residual); 0: round-1 epilogue
     int stage_off;     // epi_mode 1: byte offset of the 64 KB output / residual staging area (after the weight stages)
 };
@@ -402,7 +405,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             ga = rstd;
                             gb = rstd * mean;
                         }
-                        info = make_float4(ga, gb, (float)(cy * 3 + cx), 0.f);
+                        info = make_float4(ga, gb, (float)(cy * 3 + cx), (float)f);  // frame index: exact in fp32 (< 2^24)
                     } else {
                         info.z = -1.f;
                     }
@@ -470,6 +473,13 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                                 b0 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0));
                                 b1 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0) + 1);
                             }
+                            const size_t fidx = (size_t)info.w;
+                            if (p.Ef) {  // per-frame fold table (two-norm composition): out = ga * acc + Ef[f][cls][c]
+                                const float4* e = reinterpret_cast<const float4*>(p.Ef + (fidx * 9 + cls) * 128 + c0);
+                                a0 = a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                b0 = __ldg(e);
+                                b1 = __ldg(e + 1);
+                            }
                             float v[8] = {fmaf(info.x, t0.x, fmaf(-info.y, a0.x, b0.x)), fmaf(info.x, t0.y, fmaf(-info.y, a0.y, b0.y)),
                                           fmaf(info.x, t0.z, fmaf(-info.y, a0.z, b0.z)), fmaf(info.x, t0.w, fmaf(-info.y, a0.w, b0.w)),
                                           fmaf(info.x, t1.x, fmaf(-info.y, a1.x, b1.x)), fmaf(info.x, t1.y, fmaf(-info.y, a1.y, b1.y)),
@@ -480,8 +490,16 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             }
                             if (p.residual) {
                                 const uint4 rr = rres[i];
-                                v[0] += bf16_lo(rr.x); v[1] += bf16_hi(rr.x); v[2] += bf16_lo(rr.y); v[3] += bf16_hi(rr.y);
-                                v[4] += bf16_lo(rr.z); v[5] += bf16_hi(rr.z); v[6] += bf16_lo(rr.w); v[7] += bf16_hi(rr.w);
+                                float r8[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y), bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
+                                if (p.res_scale) {  // residual stream recomputed from the un-normalised tensor: a[f][c] * r + b[f][c]
+                                    const float4* ra = reinterpret_cast<const float4*>(p.res_scale + fidx * 128 + c0);
+                                    const float4* rb = reinterpret_cast<const float4*>(p.res_shift + fidx * 128 + c0);
+                                    const float4 x0 = __ldg(ra), x1 = __ldg(ra + 1), y0 = __ldg(rb), y1 = __ldg(rb + 1);
+                                    r8[0] = fmaf(x0.x, r8[0], y0.x); r8[1] = fmaf(x0.y, r8[1], y0.y); r8[2] = fmaf(x0.z, r8[2], y0.z); r8[3] = fmaf(x0.w, r8[3], y0.w);
+                                    r8[4] = fmaf(x1.x, r8[4], y1.x); r8[5] = fmaf(x1.y, r8[5], y1.y); r8[6] = fmaf(x1.z, r8[6], y1.z); r8[7] = fmaf(x1.w, r8[7], y1.w);
+                                }
+#pragma unroll
+                                for (int e8 = 0; e8 < 8; ++e8) v[e8] += r8[e8];
                             }
                             if (p.relu == 2) {
 #pragma unroll
@@ -584,6 +602,10 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     p.stat_part = a->stat_part;
+    p.Ef = a->Ef; p.res_scale = a->res_scale; p.res_shift = a->res_shift;
+    VPT_CHECK(!a->Ef || a->mr, "vpt_conv3x3_zp: Ef needs mr = (0, rstd) per frame");
+    VPT_CHECK(!a->res_scale == !a->res_shift && (!a->res_scale || a->residual), "vpt_conv3x3_zp: res_scale / res_shift come as a pair, with a residual");
+    VPT_CHECK(!(p.epi_mode == 1 && (a->Ef || a->res_scale)), "vpt_conv3x3_zp: the fragment-epilogue experiment (swap mode 4) does not implement Ef / res_scale");
     p.dbg_skip_epilogue = (g_cz_swap == 2) ? 2 : 0;  // 2: no epilogue work (MMA-rate experiment)
     static bool attr_set = false;
     if (!attr_set) {

@@ -101,8 +101,10 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// chan_part (optional, needs 256 % C8 == 0 so that a thread keeps one channel group): float2 [F][gridDim.x][C] per-CHANNEL (sum, sumsq)
+// partials of the pooled values -- what the two-norm composition (vpt_norm2_fold) needs instead of a normalisation pass.
 __global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
-                                                           float2* __restrict__ stat_part, int H, int W, int C8, int zp) {
+                                                           float2* __restrict__ stat_part, float2* __restrict__ chan_part, int H, int W, int C8, int zp) {
     const int Ho = H >> 1, Wo = W >> 1;
     const int ipitch = W + zp, opitch = Wo + zp;  // ZP layout: one extra zero column (and row) per frame
     const long long f = blockIdx.y;
@@ -110,6 +112,9 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict
     const uint4* fin = in + f * (long long)(H + zp) * ipitch * C8;
     uint4* fout = out + f * (long long)items;
     float s = 0.f, ss = 0.f;
+    float cs[8], css[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] = css[j] = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
         const int c = i % C8, px = (i / C8) % opitch, py = i / (C8 * opitch);
         uint4 m = make_uint4(0, 0, 0, 0);  // inputs are >= 0 (post-ReLU), so 0 == -inf padding
@@ -137,12 +142,94 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict
             const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
             s += a + b;
             ss = fmaf(a, a, fmaf(b, b, ss));
+            cs[2 * q] += a; css[2 * q] = fmaf(a, a, css[2 * q]);
+            cs[2 * q + 1] += b; css[2 * q + 1] = fmaf(b, b, css[2 * q + 1]);
         }
+    }
+    if (chan_part) {  // deterministic block reduction over the 256 / C8 threads that share a channel group
+        __shared__ float red[256 * 16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[threadIdx.x * 16 + j] = cs[j];
+            red[threadIdx.x * 16 + 8 + j] = css[j];
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < C8 * 8; k += blockDim.x) {
+            const int c8 = k >> 3, j = k & 7;
+            float a = 0.f, b = 0.f;
+            for (int t = c8; t < 256; t += C8) {
+                a += red[t * 16 + j];
+                b += red[t * 16 + 8 + j];
+            }
+            chan_part[(f * gridDim.x + blockIdx.x) * (long long)(C8 * 8) + k] = make_float2(a, b);
+        }
+        __syncthreads();
     }
     if (stat_part) {
         const float2 r = block_sum2(s, ss);
         if (threadIdx.x == 0) stat_part[f * gridDim.x + blockIdx.x] = r;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Two-norm composition (see vpt_norm2_fold in include/vpt_b200.h): one block per frame, fp64
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) norm2_fold_kernel(const float2* __restrict__ chan_part, int NP, int C, double npix, const float* __restrict__ gn,
+                                                           const float* __restrict__ bn, const float* __restrict__ Ta, const float* __restrict__ Tb,
+                                                           const float* __restrict__ Tc, const float* __restrict__ Td, int Cout, float eps,
+                                                           float2* __restrict__ mrE, float* __restrict__ Ef, float* __restrict__ res_scale,
+                                                           float* __restrict__ res_shift) {
+    const long long f = blockIdx.x;
+    __shared__ double S[512], Q[512];
+    __shared__ double red[256];
+    const int t = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int c = t; c < C; c += 256) {
+        double a = 0.0, b = 0.0;
+        for (int p = 0; p < NP; ++p) {
+            const float2 v = chan_part[(f * NP + p) * (long long)C + c];
+            a += (double)v.x;
+            b += (double)v.y;
+        }
+        S[c] = a;
+        Q[c] = b;
+        s += a;
+        q += b;
+    }
+    auto block_sum = [&](double v) {
+        __syncthreads();
+        red[t] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (t < o) red[t] += red[t + o];
+            __syncthreads();
+        }
+        return red[0];
+    };
+    const double cnt = npix * (double)C;
+    const double sum1 = block_sum(s), sq1 = block_sum(q);
+    const double mu1 = sum1 / cnt;
+    double var1 = sq1 / cnt - mu1 * mu1;
+    if (var1 < 0.0) var1 = 0.0;
+    const double rstd1 = 1.0 / sqrt(var1 + (double)eps);
+    // x0 = a_c * y1 + b_c (the post-pool GroupNorm); its per-frame statistics follow from the per-channel sums
+    double m0 = 0.0, e0 = 0.0;
+    for (int c = t; c < C; c += 256) {
+        const double a = rstd1 * (double)gn[c], b = (double)bn[c] - mu1 * a;
+        m0 += a * S[c] + npix * b;
+        e0 += a * a * Q[c] + 2.0 * a * b * S[c] + npix * b * b;
+        res_scale[f * C + c] = (float)a;
+        res_shift[f * C + c] = (float)b;
+    }
+    const double sum0 = block_sum(m0), sq0 = block_sum(e0);
+    const double mu0 = sum0 / cnt;
+    double var0 = sq0 / cnt - mu0 * mu0;
+    if (var0 < 0.0) var0 = 0.0;
+    const double rstd0 = 1.0 / sqrt(var0 + (double)eps);
+    const double R = rstd0 * rstd1;
+    if (t == 0) mrE[f] = make_float2(0.f, (float)R);
+    for (int k = t; k < 9 * Cout; k += 256)
+        Ef[f * 9 * Cout + k] = (float)(rstd0 * (double)Ta[k] - R * mu1 * (double)Tb[k] - rstd0 * mu0 * (double)Tc[k] + (double)Td[k]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -388,14 +475,28 @@ extern "C" int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C) {
     return vpt_blocks_for((long long)(H / 2) * (W / 2) * (C / 8), 2048, 64);
 }
 
-extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp, void* stream) {
+extern "C" int vpt_norm2_fold(const float* chan_part, int32_t NP, int32_t C, int64_t npix, const float* gamma_n, const float* beta_n, const float* Ta,
+                              const float* Tb, const float* Tc, const float* Td, int32_t Cout, float eps, float* mrE, float* Ef, float* res_scale,
+                              float* res_shift, int64_t F, void* stream) {
+    using namespace vpt;
+    VPT_CHECK(chan_part && gamma_n && beta_n && Ta && Tb && Tc && Td && mrE && Ef && res_scale && res_shift && F > 0, "vpt_norm2_fold: null argument");
+    VPT_CHECK(C > 0 && C <= 512 && NP > 0 && Cout > 0, "vpt_norm2_fold: need 0 < C <= 512 (C=%d)", C);
+    norm2_fold_kernel<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(chan_part), NP, C, (double)npix, gamma_n, beta_n, Ta, Tb,
+                                                                    Tc, Td, Cout, eps, reinterpret_cast<float2*>(mrE), Ef, res_scale, res_shift);
+    VPT_LAUNCH_CHECK();
+    return VPT_OK;
+}
+
+extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, float* chan_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp,
+                              void* stream) {
     using namespace vpt;
     VPT_CHECK(in && out && F > 0, "vpt_maxpool3s2: null argument");
+    VPT_CHECK(!chan_part || (C >= 8 && 256 % (C / 8) == 0), "vpt_maxpool3s2: per-channel partials need C/8 to divide 256 (C=%d)", C);
     VPT_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vpt_maxpool3s2: need even H, W and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
     VPT_CHECK(F <= 65535, "vpt_maxpool3s2: at most 65535 frames per call (got %d)", F);
     dim3 grid(vpt_pool_stat_parts(H, W, C), F);
     maxpool3s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
-                                                            reinterpret_cast<float2*>(stat_part), H, W, C / 8, zp ? 1 : 0);
+                                                            reinterpret_cast<float2*>(stat_part), reinterpret_cast<float2*>(chan_part), H, W, C / 8, zp ? 1 : 0);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

@@ -87,7 +87,8 @@ def stats_finalize(part, G, n_per_group, count, eps=1e-5):
     return mr
 
 
-def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True, out=None):
+def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None, want_stats=True, out=None, Ef=None, res_scale=None,
+               res_shift=None):
     """GroupNorm(1)->conv3x3->ReLU[+residual] on a ZP tensor x bf16 [F,H+1,W+1,Cin]; returns (ZP out, per-frame (mean, rstd))."""
     _cuda(x, Wb)
     F_, Cin = x.shape[0], x.shape[3]
@@ -104,6 +105,7 @@ def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None,
     a = nat.ConvZpArgs()
     a.x, a.w, a.F, a.H, a.W, a.Cin, a.Cout = _p(x), _p(Wb), F_, H, W, Cin, Cout
     a.mr, a.S1, a.S2, a.relu, a.residual, a.out, a.stat_part = _p(mr), _p(S1), _p(S2), relu, _p(residual), _p(out), _p(part)
+    a.Ef, a.res_scale, a.res_shift = _p(Ef), _p(res_scale), _p(res_shift)  # two-norm composition (vpt_norm2_fold)
     prof = GEMM_PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -123,8 +125,10 @@ def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None,
     return out, mr_out
 
 
-def firstconv_pool(img, w, bias, C0, zp=True, out_f32=False):
-    """img u8 [F,H,W,3] -> (bf16 (fp32 with out_f32) [F,H/2(+1),W/2(+1),C0] (ZP layout when zp), per-frame (mean, rstd))."""
+def firstconv_pool(img, w, bias, C0, zp=True, out_f32=False, want_chan=False):
+    """img u8 [F,H,W,3] -> (bf16 (fp32 with out_f32) [F,H/2(+1),W/2(+1),C0] (ZP layout when zp), per-frame (mean, rstd)).
+    want_chan: also return the per-channel (sum, sumsq) partials [F, NP, C0, 2] of the pooled tensor (None if the kernel that ran does
+    not produce them), for `norm2_fold`."""
     _cuda(img, w, bias)
     F_, H, W, _ = img.shape
     z = int(zp)
@@ -133,7 +137,10 @@ def firstconv_pool(img, w, bias, C0, zp=True, out_f32=False):
     part = torch.empty((F_, P, 2), dtype=F32, device=img.device)
     nat.check(nat.lib().vpt_firstconv_pool(_p(img), _p(w), _p(bias), _p(out), _p(part), F_, H, W, C0, z, int(out_f32), _stream()), "vpt_firstconv_pool")
     _count()
-    return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * C0)
+    mr = stats_finalize(part, F_, P, (H // 2) * (W // 2) * C0)
+    if want_chan:  # the tcgen05 kernel's partials are per (8 pooled rows, column half, channel)
+        return out, mr, (part.view(F_, P // C0, C0, 2) if P % C0 == 0 and P >= C0 else None)
+    return out, mr
 
 
 def conv3d_t5(img, w, bias, C, out_f32=False):
@@ -203,17 +210,37 @@ def attention_f32(q, full_k, full_v, R, b_nd, first_u8, smask_u8, B, t, maxlen, 
     return out
 
 
-def maxpool3s2(x, zp=True):
-    """bf16 [F,H,W,C] (>= 0) -> (bf16 [F,H/2,W/2,C], per-frame (mean, rstd)); with zp both tensors are ZP ([F,H+1,W+1,C])."""
+def maxpool3s2(x, zp=True, want_chan=False):
+    """bf16 [F,H,W,C] (>= 0) -> (bf16 [F,H/2,W/2,C], per-frame (mean, rstd)); with zp both tensors are ZP ([F,H+1,W+1,C]).
+    want_chan: also the per-channel (sum, sumsq) partials [F, NP, C, 2] of the pooled tensor (None when C/8 does not divide 256)."""
     _cuda(x)
     z = int(zp)
     F_, H, W, Cc = x.shape[0], x.shape[1] - z, x.shape[2] - z, x.shape[3]
     out = torch.empty((F_, H // 2 + z, W // 2 + z, Cc), dtype=BF16, device=x.device)
     P = nat.lib().vpt_pool_stat_parts(H, W, Cc)
     part = torch.empty((F_, P, 2), dtype=F32, device=x.device)
-    nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), F_, H, W, Cc, z, _stream()), "vpt_maxpool3s2")
+    chan = torch.empty((F_, P, Cc, 2), dtype=F32, device=x.device) if (want_chan and Cc >= 8 and 256 % (Cc // 8) == 0) else None
+    nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), _p(chan), F_, H, W, Cc, z, _stream()), "vpt_maxpool3s2")
     _count()
-    return out, stats_finalize(part, F_, P, (H // 2) * (W // 2) * Cc)
+    mr = stats_finalize(part, F_, P, (H // 2) * (W // 2) * Cc)
+    return (out, mr, chan) if want_chan else (out, mr)
+
+
+def norm2_fold(chan_part, npix, gamma_n, beta_n, tabs):
+    """Two-norm composition tables (vpt_norm2_fold): chan_part fp32 [F, NP, C, 2]; tabs = (Ta, Tb, Tc, Td) each fp32 [9, Cout] ->
+    (mrE [F, 2], Ef [F, 9, Cout], res_scale [F, C], res_shift [F, C])."""
+    _cuda(chan_part, gamma_n, beta_n, *tabs)
+    F_, NP, Cc, _ = chan_part.shape
+    Cout = tabs[0].shape[1]
+    dev = chan_part.device
+    mrE = torch.empty((F_, 2), dtype=F32, device=dev)
+    Ef = torch.empty((F_, 9, Cout), dtype=F32, device=dev)
+    rs = torch.empty((F_, Cc), dtype=F32, device=dev)
+    rb = torch.empty((F_, Cc), dtype=F32, device=dev)
+    nat.check(nat.lib().vpt_norm2_fold(_p(chan_part), NP, Cc, npix, _p(gamma_n), _p(beta_n), _p(tabs[0]), _p(tabs[1]), _p(tabs[2]), _p(tabs[3]), Cout, 1e-5,
+                                       _p(mrE), _p(Ef), _p(rs), _p(rb), F_, _stream()), "vpt_norm2_fold")
+    _count()
+    return mrE, Ef, rs, rb
 
 
 def affine_norm(x, mr, gamma, beta, rows_per_group, want_stats=False, want_f32=False):

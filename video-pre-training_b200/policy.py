@@ -236,6 +236,22 @@ def _fold_conv(W, gamma, beta):
     return Wb.reshape(Cout, -1).contiguous(), S1, S2
 
 
+def _fold_conv2(W, gamma0, beta0, gamma_n, beta_n):
+    """Two-norm composition for block 0's conv0 (x0 = GN_n(y1) is not materialised; the conv reads y1):
+    conv(GN_0(GN_n(y1))) = R * conv_{W g0 gn}(y1) + rstd0*Ta - R*mu1*Tb - rstd0*mu0*Tc + Td   per border class (see vpt_norm2_fold).
+    Returns (bf16 weights [Cout, 9*Cin], (Ta, Tb, Tc, Td) fp32 [9, Cout]); Tb is summed from the bf16-rounded weights."""
+    Cout = W.shape[0]
+    Wb = (W * (gamma0 * gamma_n)[None, :, None, None]).permute(0, 2, 3, 1).contiguous().to(BF16)  # [Cout, ky, kx, Cin]
+    M = _class_taps(W.device)
+    per_tap = lambda v: v.reshape(Cout, 9)
+    tb = per_tap(Wb.sum(-1, dtype=torch.float64))
+    ta = per_tap((W * (gamma0 * beta_n)[None, :, None, None]).sum(1, dtype=torch.float64))
+    tc = per_tap((W * gamma0[None, :, None, None]).sum(1, dtype=torch.float64))
+    td = per_tap((W * beta0[None, :, None, None]).sum(1, dtype=torch.float64))
+    tabs = tuple((M @ t.t()).float().contiguous() for t in (ta, tb, tc, td))
+    return Wb.reshape(Cout, -1).contiguous(), tabs
+
+
 def _fold_linear(W, gamma=None, beta=None, bias=None):
     """[LayerNorm ->] Linear fold: out = rstd*(x @ (W*gamma)^T) - rstd*mean*S1 + S2, S2 = W @ beta (+ bias)."""
     Wg = W if gamma is None else W * gamma[None, :]
@@ -270,6 +286,8 @@ class _Prepared:
             else:
                 st["first"] = _fold_conv(g(f"{s}.firstconv.layer.weight"), g(f"{s}.firstconv.norm.weight"), g(f"{s}.firstconv.norm.bias"))
             st["n_g"], st["n_b"] = g(f"{s}.n.weight").float().contiguous(), g(f"{s}.n.bias").float().contiguous()
+            q0 = f"{s}.blocks.0.conv0"
+            st["conv0n"] = _fold_conv2(g(f"{q0}.layer.weight"), g(f"{q0}.norm.weight"), g(f"{q0}.norm.bias"), g(f"{s}.n.weight"), g(f"{s}.n.bias"))
             st["convs"] = []
             for j in range(2):
                 for k in range(2):
@@ -323,6 +341,7 @@ class MinecraftPolicy(nn.Module):
     """lib/policy.py:83-224.  `forward(ob, state_in, context)` -> ((pi_latent, vf_latent), state_out)."""
 
     cnn_chunk_frames = 2048  # frames per CNN pass (bounds the activation workspace: ~5 MiB/frame at 2x width)
+    fold_stack_norm = True   # inference: fold the post-pool GroupNorm of every stack into block 0 (no `affine_norm_zp` pass)
     idm_chunk_frames = 512   # IDM: ~13 MiB/frame at 4x width (conv3d output + full-resolution first conv)
 
     def __init__(self, **policy_kwargs):
@@ -387,24 +406,40 @@ class MinecraftPolicy(nn.Module):
         for i, c in enumerate(cfg.chans):
             st = prep.stacks[i]
             rec = dict(x_in=x, mr_in=mr, H_in=H, W_in=W, full=None, blocks=[]) if tape is not None else None
+            fold = self.fold_stack_norm and rec is None  # inference: the post-pool GroupNorm is folded into its two consumers
             if i == 0 and "fc_w" in st:
-                y1, mr1 = ops.firstconv_pool(img, st["fc_w"], st["fc_b"], c, zp=True)
+                y1, mr1, chan = ops.firstconv_pool(img, st["fc_w"], st["fc_b"], c, zp=True, want_chan=True)
             else:
                 Wb, S1, S2 = st["first"]
                 full, _ = ops.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1, want_stats=False)
-                y1, mr1 = ops.maxpool3s2(full, zp=True)
+                y1, mr1, chan = ops.maxpool3s2(full, zp=True, want_chan=True)
                 if rec is not None:
                     rec["full"] = full
                 del full
             H, W = H // 2, W // 2
             self._tap(f"{pfx}.stacks.{i}.pool", y1)
-            # post-pool GroupNorm `n` (lib/impala_cnn.py:119): materialised because it is the residual stream
-            x, mr = ops.affine_norm_zp(y1, mr1, st["n_g"], st["n_b"])
-            if rec is not None:
-                rec.update(y1=y1, mr1=mr1, x0=x, mr0=mr)
-            del y1
-            self._tap(f"{pfx}.stacks.{i}.n", x)
-            for j in range(2):
+            if fold and chan is not None:
+                # two-norm composition (vpt_norm2_fold): x0 = n(y1) is never written; block 0 reads y1 with per-frame fold tables
+                Wb0, tabs = st["conv0n"]
+                mrE, Ef, rs, rb = ops.norm2_fold(chan, H * W, st["n_g"], st["n_b"], tabs)
+                del chan
+                hmid, mrh = ops.conv3x3_zp(y1, Wb0, H, W, mr=mrE, Ef=Ef, relu=1)
+                self._tap(f"{pfx}.stacks.{i}.blocks.0.conv0", hmid)
+                Wb, S1, S2 = st["convs"][1]
+                x, mr = ops.conv3x3_zp(hmid, Wb, H, W, mr=mrh, S1=S1, S2=S2, relu=1, residual=y1, res_scale=rs, res_shift=rb)
+                del y1, hmid
+                self._tap(f"{pfx}.stacks.{i}.blocks.0", x)
+                first_block = 1
+            else:
+                # post-pool GroupNorm `n` (lib/impala_cnn.py:119) as a pass: the training tape needs x0, and so do shapes whose pool
+                # kernel cannot produce per-channel sums
+                x, mr = ops.affine_norm_zp(y1, mr1, st["n_g"], st["n_b"])
+                if rec is not None:
+                    rec.update(y1=y1, mr1=mr1, x0=x, mr0=mr)
+                del y1
+                self._tap(f"{pfx}.stacks.{i}.n", x)
+                first_block = 0
+            for j in range(first_block, 2):
                 Wb, S1, S2 = st["convs"][2 * j]
                 hmid, mrh = ops.conv3x3_zp(x, Wb, H, W, mr=mr, S1=S1, S2=S2, relu=1)
                 self._tap(f"{pfx}.stacks.{i}.blocks.{j}.conv0", hmid)
