@@ -215,7 +215,9 @@ int vpt_conv3d_stat_parts(int32_t H, int32_t W, int32_t C);
  *   in [F][H][W][C] -> out [F][H/2][W/2][C]   (zp=1: both in the ZP layout, [F][H+1][W+1][C] -> [F][H/2+1][W/2+1][C])
  *   stat_part float2 [F][vpt_pool_stat_parts()] */
 int vpt_maxpool3s2(const void* in, void* out, float* stat_part, float* chan_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp,
-                   void* stream);  /* chan_part: NULL or float2 [F][vpt_pool_stat_parts(H, W, C)][C] per-channel partials (needs C/8 | 256) */
+                   void* stream);  /* chan_part: NULL or float2 [F][P][C] per-channel partials (needs C/8 | 256); with chan_part BOTH partial
+                                      buffers hold P = vpt_pool_chan_parts(H, W, C) entries per frame instead of vpt_pool_stat_parts */
+int vpt_pool_chan_parts(int32_t H, int32_t W, int32_t C);
 /* Two-norm composition: the post-pool GroupNorm `n` (lib/impala_cnn.py:119) is not run as a pass; its effect is folded into the two
  * consumers of x0 = n(y1): block 0's conv0 (input y1, weights W*gamma0*gamma_n, per-frame table Ef) and conv1 (residual y1 with a
  * per-frame affine).  From the per-channel (sum, sumsq) partials of y1 [F][NP][C] (vpt_firstconv_pool / vpt_maxpool3s2), gamma_n / beta_n

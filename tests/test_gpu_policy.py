@@ -122,7 +122,7 @@ def test_chunk_invariance_and_reset_on_gpu():
             acc.append(pd["camera"])
         outs.append(torch.cat(acc, 1))
     print(f"chunk invariance: max abs diff of the camera log-probs {(outs[0] - outs[1]).abs().max().item():.3e}")
-    assert (outs[0] - outs[1]).abs().max() < 3e-2
+    assert (outs[0] - outs[1]).abs().max() < 2e-2  # measured 6.5e-3
     first = torch.zeros(B, 8, dtype=torch.bool, device=DEV)
     first[:, 0] = True
     (pd1, _, _), _ = pol({"img": img[:, 8:]}, first, st)

@@ -102,6 +102,7 @@ SIGNATURES = {
     "vpt_maxpool3s2": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vpt_norm2_fold": (_I, [_P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _L, _P]),
     "vpt_pool_stat_parts": (_I, [_I, _I, _I]),
+    "vpt_pool_chan_parts": (_I, [_I, _I, _I]),
     "vpt_affine_norm": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "vpt_affine_norm_zp": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vpt_norm_stat_parts": (_I, [_I, _I]),

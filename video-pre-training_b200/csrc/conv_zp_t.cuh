@@ -66,6 +66,9 @@ __device__ __forceinline__ float transpose_reduce32(float (&x)[32], int lane) {
     return x[0];
 }
 
+// kFold (compile time, so that the plain variant's epilogue -- the co-bottleneck of this kernel -- is untouched by the extra code):
+// 0 = plain (S1 / S2 class tables), 1 = per-frame fold table Ef, 2 = plain fold + affine residual (two-norm composition, vpt_norm2_fold)
+template <int kFold>
 __global__ void __launch_bounds__(kCzThreads, 1)
 conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmR, const ConvZpTParams p) {
@@ -381,11 +384,18 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             // reads are bank-conflict free.  Each warp does 4 passes per quarter; residual rows are prefetched a quarter ahead.
             const int chunk = lane >> 1, c0 = chunk * 8;
             // fold tables of the interior border class (cls 4: ~94 % of the rows) for this thread's 8 channels, kept in registers
-            float s1c[8], s2c[8];
+            // (two-norm composition: the tables are per FRAME; the registers hold those of the tile's first frame fA, rows of a second
+            //  frame -- 6 % of the tiles touch one -- and border rows take the global-load path)
+            const size_t fA = kFold ? (size_t)((tile * kCtPix) / p.FS) : 0;
+            float s1c[8], s2c[8], rac[kFold == 2 ? 8 : 1], rbc[kFold == 2 ? 8 : 1];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                s1c[j] = p.S1 ? __ldg(p.S1 + 4 * 128 + c0 + j) : 0.f;
-                s2c[j] = p.S2 ? __ldg(p.S2 + 4 * 128 + c0 + j) : 0.f;
+                s1c[j] = (kFold != 1 && p.S1) ? __ldg(p.S1 + 4 * 128 + c0 + j) : 0.f;
+                s2c[j] = kFold == 1 ? __ldg(p.Ef + (fA * 9 + 4) * 128 + c0 + j) : (p.S2 ? __ldg(p.S2 + 4 * 128 + c0 + j) : 0.f);
+                if (kFold == 2) {
+                    rac[j] = __ldg(p.res_scale + fA * 128 + c0 + j);
+                    rbc[j] = __ldg(p.res_shift + fA * 128 + c0 + j);
+                }
             }
             // per-row constants (ga, gb, cls; cls -1 = zero row/column, -2 = beyond the tensor) of quarter hh of tile tl, written by
             // the first 64 epilogue threads into buffer hh & 1 ONE QUARTER AHEAD of its use (the statistics loads overlap phase B)
@@ -405,7 +415,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             ga = rstd;
                             gb = rstd * mean;
                         }
-                        info = make_float4(ga, gb, (float)(cy * 3 + cx), (float)f);  // frame index: exact in fp32 (< 2^24)
+                        info = make_float4(ga, gb, (float)(cy * 3 + cx), kFold ? (float)f : 0.f);  // frame index: exact in fp32 (< 2^24)
                     } else {
                         info.z = -1.f;
                     }
@@ -465,18 +475,17 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             const float4 t1 = *reinterpret_cast<const float4*>(s_tile + prow * kCtPitch + c0 + 4);
                             float4 a0 = make_float4(s1c[0], s1c[1], s1c[2], s1c[3]), a1 = make_float4(s1c[4], s1c[5], s1c[6], s1c[7]);
                             float4 b0 = make_float4(s2c[0], s2c[1], s2c[2], s2c[3]), b1 = make_float4(s2c[4], s2c[5], s2c[6], s2c[7]);
-                            if (cls != 4 && p.S1) {
+                            if (kFold != 1 && cls != 4 && p.S1) {
                                 a0 = __ldg(reinterpret_cast<const float4*>(p.S1 + cls * 128 + c0));
                                 a1 = __ldg(reinterpret_cast<const float4*>(p.S1 + cls * 128 + c0) + 1);
                             }
-                            if (cls != 4 && p.S2) {
+                            if (kFold != 1 && cls != 4 && p.S2) {
                                 b0 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0));
                                 b1 = __ldg(reinterpret_cast<const float4*>(p.S2 + cls * 128 + c0) + 1);
                             }
-                            const size_t fidx = (size_t)info.w;
-                            if (p.Ef) {  // per-frame fold table (two-norm composition): out = ga * acc + Ef[f][cls][c]
+                            const size_t fidx = kFold ? (size_t)info.w : 0;
+                            if (kFold == 1 && (cls != 4 || fidx != fA)) {  // per-frame fold table: out = ga * acc + Ef[f][cls][c]
                                 const float4* e = reinterpret_cast<const float4*>(p.Ef + (fidx * 9 + cls) * 128 + c0);
-                                a0 = a1 = make_float4(0.f, 0.f, 0.f, 0.f);
                                 b0 = __ldg(e);
                                 b1 = __ldg(e + 1);
                             }
@@ -491,12 +500,17 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             if (p.residual) {
                                 const uint4 rr = rres[i];
                                 float r8[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y), bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
-                                if (p.res_scale) {  // residual stream recomputed from the un-normalised tensor: a[f][c] * r + b[f][c]
-                                    const float4* ra = reinterpret_cast<const float4*>(p.res_scale + fidx * 128 + c0);
-                                    const float4* rb = reinterpret_cast<const float4*>(p.res_shift + fidx * 128 + c0);
-                                    const float4 x0 = __ldg(ra), x1 = __ldg(ra + 1), y0 = __ldg(rb), y1 = __ldg(rb + 1);
-                                    r8[0] = fmaf(x0.x, r8[0], y0.x); r8[1] = fmaf(x0.y, r8[1], y0.y); r8[2] = fmaf(x0.z, r8[2], y0.z); r8[3] = fmaf(x0.w, r8[3], y0.w);
-                                    r8[4] = fmaf(x1.x, r8[4], y1.x); r8[5] = fmaf(x1.y, r8[5], y1.y); r8[6] = fmaf(x1.z, r8[6], y1.z); r8[7] = fmaf(x1.w, r8[7], y1.w);
+                                if (kFold == 2) {  // residual stream recomputed from the un-normalised tensor: a[f][c] * r + b[f][c]
+                                    if (fidx == fA) {
+#pragma unroll
+                                        for (int e8 = 0; e8 < 8; ++e8) r8[e8] = fmaf(rac[e8], r8[e8], rbc[e8]);
+                                    } else {
+                                        const float4* ra = reinterpret_cast<const float4*>(p.res_scale + fidx * 128 + c0);
+                                        const float4* rb = reinterpret_cast<const float4*>(p.res_shift + fidx * 128 + c0);
+                                        const float4 x0 = __ldg(ra), x1 = __ldg(ra + 1), y0 = __ldg(rb), y1 = __ldg(rb + 1);
+                                        r8[0] = fmaf(x0.x, r8[0], y0.x); r8[1] = fmaf(x0.y, r8[1], y0.y); r8[2] = fmaf(x0.z, r8[2], y0.z); r8[3] = fmaf(x0.w, r8[3], y0.w);
+                                        r8[4] = fmaf(x1.x, r8[4], y1.x); r8[5] = fmaf(x1.y, r8[5], y1.y); r8[6] = fmaf(x1.z, r8[6], y1.z); r8[7] = fmaf(x1.w, r8[7], y1.w);
+                                    }
                                 }
 #pragma unroll
                                 for (int e8 = 0; e8 < 8; ++e8) v[e8] += r8[e8];
@@ -609,13 +623,18 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     p.dbg_skip_epilogue = (g_cz_swap == 2) ? 2 : 0;  // 2: no epilogue work (MMA-rate experiment)
     static bool attr_set = false;
     if (!attr_set) {
-        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     long long grid = num_sms();
     if (grid <= 0) grid = 148;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    conv3x3_zp_t_kernel<<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
+    VPT_CHECK(!(a->Ef && a->res_scale), "vpt_conv3x3_zp: Ef and res_scale are not combined (Cout == 128 kernel)");
+    if (a->Ef) conv3x3_zp_t_kernel<1><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
+    else if (a->res_scale) conv3x3_zp_t_kernel<2><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
+    else conv3x3_zp_t_kernel<0><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

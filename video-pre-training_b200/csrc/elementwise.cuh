@@ -103,7 +103,8 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 
 // chan_part (optional, needs 256 % C8 == 0 so that a thread keeps one channel group): float2 [F][gridDim.x][C] per-CHANNEL (sum, sumsq)
 // partials of the pooled values -- what the two-norm composition (vpt_norm2_fold) needs instead of a normalisation pass.
-__global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+template <bool CHAN>
+__global__ void __launch_bounds__(256, CHAN ? 6 : 8) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                            float2* __restrict__ stat_part, float2* __restrict__ chan_part, int H, int W, int C8, int zp) {
     const int Ho = H >> 1, Wo = W >> 1;
     const int ipitch = W + zp, opitch = Wo + zp;  // ZP layout: one extra zero column (and row) per frame
@@ -140,13 +141,21 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
-            s += a + b;
-            ss = fmaf(a, a, fmaf(b, b, ss));
-            cs[2 * q] += a; css[2 * q] = fmaf(a, a, css[2 * q]);
-            cs[2 * q + 1] += b; css[2 * q + 1] = fmaf(b, b, css[2 * q + 1]);
+            if (CHAN) {  // per-channel sums; the frame sums are their total
+                cs[2 * q] += a; css[2 * q] = fmaf(a, a, css[2 * q]);
+                cs[2 * q + 1] += b; css[2 * q + 1] = fmaf(b, b, css[2 * q + 1]);
+            } else {
+                s += a + b;
+                ss = fmaf(a, a, fmaf(b, b, ss));
+            }
         }
     }
-    if (chan_part) {  // deterministic block reduction over the 256 / C8 threads that share a channel group
+    if (CHAN) {  // deterministic block reduction over the 256 / C8 threads that share a channel group
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s += cs[j];
+            ss += css[j];
+        }
         __shared__ float red[256 * 16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -474,6 +483,12 @@ static inline int vpt_blocks_for(long long items, int per_block, int cap) {
 extern "C" int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C) {
     return vpt_blocks_for((long long)(H / 2) * (W / 2) * (C / 8), 2048, 64);
 }
+/* With per-channel partials every block ends with a 16 KB shared-memory reduction: 4x fewer, 4x longer blocks amortise it
+ * (measured: the pool was 50 % slower with the per-frame block count above). */
+extern "C" int vpt_pool_chan_parts(int32_t H, int32_t W, int32_t C) {
+    const int p = vpt_pool_stat_parts(H, W, C) / 4;
+    return p < 1 ? 1 : p;
+}
 
 extern "C" int vpt_norm2_fold(const float* chan_part, int32_t NP, int32_t C, int64_t npix, const float* gamma_n, const float* beta_n, const float* Ta,
                               const float* Tb, const float* Tc, const float* Td, int32_t Cout, float eps, float* mrE, float* Ef, float* res_scale,
@@ -494,9 +509,13 @@ extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, float
     VPT_CHECK(!chan_part || (C >= 8 && 256 % (C / 8) == 0), "vpt_maxpool3s2: per-channel partials need C/8 to divide 256 (C=%d)", C);
     VPT_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vpt_maxpool3s2: need even H, W and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
     VPT_CHECK(F <= 65535, "vpt_maxpool3s2: at most 65535 frames per call (got %d)", F);
-    dim3 grid(vpt_pool_stat_parts(H, W, C), F);
-    maxpool3s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
-                                                            reinterpret_cast<float2*>(stat_part), reinterpret_cast<float2*>(chan_part), H, W, C / 8, zp ? 1 : 0);
+    dim3 grid(chan_part ? vpt_pool_chan_parts(H, W, C) : vpt_pool_stat_parts(H, W, C), F);
+    if (chan_part)
+        maxpool3s2_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
+                                                                      reinterpret_cast<float2*>(stat_part), reinterpret_cast<float2*>(chan_part), H, W, C / 8, zp ? 1 : 0);
+    else
+        maxpool3s2_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
+                                                                       reinterpret_cast<float2*>(stat_part), nullptr, H, W, C / 8, zp ? 1 : 0);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

@@ -217,9 +217,10 @@ def maxpool3s2(x, zp=True, want_chan=False):
     z = int(zp)
     F_, H, W, Cc = x.shape[0], x.shape[1] - z, x.shape[2] - z, x.shape[3]
     out = torch.empty((F_, H // 2 + z, W // 2 + z, Cc), dtype=BF16, device=x.device)
-    P = nat.lib().vpt_pool_stat_parts(H, W, Cc)
+    with_chan = want_chan and Cc >= 8 and 256 % (Cc // 8) == 0
+    P = nat.lib().vpt_pool_chan_parts(H, W, Cc) if with_chan else nat.lib().vpt_pool_stat_parts(H, W, Cc)
     part = torch.empty((F_, P, 2), dtype=F32, device=x.device)
-    chan = torch.empty((F_, P, Cc, 2), dtype=F32, device=x.device) if (want_chan and Cc >= 8 and 256 % (Cc // 8) == 0) else None
+    chan = torch.empty((F_, P, Cc, 2), dtype=F32, device=x.device) if with_chan else None
     nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), _p(chan), F_, H, W, Cc, z, _stream()), "vpt_maxpool3s2")
     _count()
     mr = stats_finalize(part, F_, P, (H // 2) * (W // 2) * Cc)
