@@ -104,7 +104,7 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // chan_part (optional, needs 256 % C8 == 0 so that a thread keeps one channel group): float2 [F][gridDim.x][C] per-CHANNEL (sum, sumsq)
 // partials of the pooled values -- what the two-norm composition (vpt_norm2_fold) needs instead of a normalisation pass.
 template <bool CHAN>
-__global__ void __launch_bounds__(256, CHAN ? 6 : 8) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                            float2* __restrict__ stat_part, float2* __restrict__ chan_part, int H, int W, int C8, int zp) {
     const int Ho = H >> 1, Wo = W >> 1;
     const int ipitch = W + zp, opitch = Wo + zp;  // ZP layout: one extra zero column (and row) per frame

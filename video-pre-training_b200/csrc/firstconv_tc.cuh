@@ -47,6 +47,10 @@ struct FirstconvTcParams {
     int b_stages;
     int frame_stride;    // bytes between the two frame buffers
     long long items;     // F * nbands * ncb
+    // backward variant (firstconv_tc_kernel<W, false, true>): gradient of the fused conv + ReLU + max-pool wrt weights and bias
+    const __nv_bfloat16* dy;  // bf16 ZP [F][H/2+1][W/2+1][C0]
+    float* bwd_ws;            // [gridDim.x * 2][C0][28] partial (dW[27], db) per (CTA, column half, channel)
+    long long fb_count;       // F * nbands (backward: items are ordered channel block first: item = cb * fb_count + fb)
 };
 
 template <int N>
@@ -105,8 +109,14 @@ struct FtItem {
 };
 __device__ __forceinline__ FtItem ft_item(const FirstconvTcParams& p, long long item) {
     FtItem it;
-    it.cb = (int)(item % p.ncb);
-    const long long fb = item / p.ncb;
+    long long fb;
+    if (p.dy != nullptr) {  // backward: channel block outermost, so that a CTA's accumulators change block at most once
+        it.cb = (int)(item / p.fb_count);
+        fb = item - (long long)it.cb * p.fb_count;
+    } else {
+        it.cb = (int)(item % p.ncb);
+        fb = item / p.ncb;
+    }
     it.band = (int)(fb % p.nbands);
     it.f = fb / p.nbands;
     it.t0 = it.band * p.band_rows - (it.band > 0 ? 1 : 0);
@@ -151,7 +161,7 @@ __device__ __forceinline__ void ft_pool_chunk(const float (&a)[CW], const float 
     lb = b[CW - 1];
 }
 
-template <int W, bool F32OUT>
+template <int W, bool F32OUT, bool BWD>
 __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const FirstconvTcParams p) {
     constexpr int NPOS = 2 * W;           // UMMA N: two conv rows
     constexpr int CW = 16;                // columns per epilogue chunk
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const First
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&fr_full[i], 1);
-            mbar_init(&fr_empty[i], kFtProdWarps);
+            mbar_init(&fr_empty[i], kFtProdWarps + (BWD ? kFtEpiWarps : 0));  // backward: the epilogue warps gather patches from the frame too
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], kFtEpiWarps);
         }
@@ -331,6 +341,136 @@ __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const First
             __syncwarp();
             if (lane == 0) mbar_arrive(&fr_empty[buf]);  // this warp is done reading the frame
         }
+    } else if (BWD) {
+        // ================= backward epilogue (warps 0..7): thread = output channel =================
+        // The conv map is recomputed on the tensor core exactly like the forward; per pooled output the thread finds the FIRST maximum
+        // of its 3x3 window (row-major, positions outside the image excluded: max_pool2d pads with -inf), applies the ReLU mask
+        // (only a positive maximum passes a gradient), reads dy and accumulates  dW[k] += g * patch(argmax)[k],  db += g  in registers;
+        // the 27 patch values are gathered from the u8 frame in shared memory with the builders' aligned-window / PRMT / 2^23 trick.
+        const int quarter = warp & 3, half = warp >> 2;
+        const int x0 = half * (W / 2);
+        const int Ho = H / 2, Wo = W / 2;
+        const int dpitch = Wo + 1;  // dy is ZP
+        float dW[27], db = 0.f;
+#pragma unroll
+        for (int k = 0; k < 27; ++k) dW[k] = 0.f;
+        int cur_cb = -1;
+        unsigned flushed = 0u;
+        auto flush = [&](int cb) {  // partial sums of channel block cb -> this CTA's slot
+            const int ch = cb * 128 + quarter * 32 + lane;
+            if (ch < p.C0) {
+                float* o = p.bwd_ws + (((size_t)blockIdx.x * 2 + half) * p.C0 + ch) * 28;
+#pragma unroll
+                for (int k = 0; k < 27; ++k) o[k] = dW[k];
+                o[27] = db;
+            }
+#pragma unroll
+            for (int k = 0; k < 27; ++k) dW[k] = 0.f;
+            db = 0.f;
+            flushed |= 1u << cb;
+        };
+        int local = 0, li = 0;
+        bool ok = true;
+        for (long long item = blockIdx.x; item < p.items && ok; item += gridDim.x, ++li) {
+            const FtItem it = ft_item(p, item);
+            if (cur_cb >= 0 && it.cb != cur_cb) flush(cur_cb);
+            cur_cb = it.cb;
+            const int ch = it.cb * 128 + quarter * 32 + lane;
+            const bool valid = ch < p.C0;
+            const int buf = li & 1;
+            const uint8_t* fr = s_frames + (size_t)buf * p.frame_stride + 16;
+            const __nv_bfloat16* fdy = p.dy + (size_t)it.f * (Ho + 1) * dpitch * p.C0 + ch;
+            float cval[NCH][CW / 2];   // horizontally reduced conv row 2t-1: value ...
+            uint32_t ccol[NCH];        // ... and which of its three columns held it (2 bits per pooled column)
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                ccol[j] = 0u;
+#pragma unroll
+                for (int k = 0; k < CW / 2; ++k) cval[j][k] = -INFINITY;
+            }
+            const bool warp_idle = it.cb * 128 + quarter * 32 >= p.C0;  // padding channels only (C0 = 64 / 192): keep the barrier protocol, skip the work
+            for (int t = it.t0; t <= it.t1 && ok; ++t, ++local) {
+                const int as = local & 1;
+                const bool emit = (t >= it.band * p.band_rows) && valid;
+                if (!(ok = mbar_wait(&tmem_full_bar[as], (uint32_t)(local >> 1) & 1u, 0x950u))) break;
+                tc_fence_after();
+                if (warp_idle) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                    continue;
+                }
+                const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols);
+                float la = -INFINITY, lb = -INFINITY;  // conv column x0 - 1 (outside the image for the left half)
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    float a[CW], b[CW];
+                    tmem_ld_cols<CW>(trow + x0 + j * CW, a);
+                    tmem_ld_cols<CW>(trow + W + x0 + j * CW, b);
+                    if (j == 0 && half == 1) {
+                        la = tmem_ld_col1(trow + x0 - 1);
+                        lb = tmem_ld_col1(trow + W + x0 - 1);
+                    }
+                    tmem_ld_wait();
+                    if (j == NCH - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                    }
+                    uint32_t ncol = 0u;
+#pragma unroll
+                    for (int k = 0; k < CW / 2; ++k) {
+                        // first maximum of the three columns 2px-1, 2px, 2px+1 in conv rows 2t (v0, i0) and 2t+1 (v1, i1)
+                        float v0 = (k == 0) ? la : a[2 * k - 1], v1 = (k == 0) ? lb : b[2 * k - 1];
+                        int i0 = 0, i1 = 0;
+                        if (a[2 * k] > v0) { v0 = a[2 * k]; i0 = 1; }
+                        if (a[2 * k + 1] > v0) { v0 = a[2 * k + 1]; i0 = 2; }
+                        if (b[2 * k] > v1) { v1 = b[2 * k]; i1 = 1; }
+                        if (b[2 * k + 1] > v1) { v1 = b[2 * k + 1]; i1 = 2; }
+                        // window rows 2t-1 (carried), 2t, 2t+1 in that order
+                        float best = cval[j][k];
+                        int br = 0, bj = (int)((ccol[j] >> (2 * k)) & 3u);
+                        if (v0 > best) { best = v0; br = 1; bj = i0; }
+                        if (v1 > best) { best = v1; br = 2; bj = i1; }
+                        cval[j][k] = v1;
+                        ncol |= (uint32_t)i1 << (2 * k);
+                        if (emit && best > 0.f) {
+                            const int px = (x0 + j * CW) / 2 + k;
+                            const float g = __bfloat162float(fdy[((size_t)t * dpitch + px) * p.C0]);
+                            const int y = 2 * t - 1 + br, x = 2 * px - 1 + bj;  // conv position that won
+                            db += g;
+                            const int b0 = 3 * x - 3, a0 = b0 & ~3;
+                            const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(b0 & 3);
+                            const uint32_t m0 = (x == 0) ? 0xFF000000u : 0xFFFFFFFFu;
+                            const uint32_t m1 = (x == W - 1) ? 0x0000FFFFu : 0xFFFFFFFFu;
+                            const uint32_t m2 = (x == W - 1) ? 0u : 0xFFFFFFFFu;
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky) {
+                                const int yy = y + ky - 1;
+                                const uint8_t* src = (yy < 0 || yy >= H) ? (s_zero + 16) : (fr + (size_t)yy * PITCH);
+                                const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + a0);
+                                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+                                const uint32_t A0 = prmt(w0, w1, sel) & m0, A1 = prmt(w1, w2, sel) & m1, A2 = prmt(w2, w2, sel) & m2;
+#pragma unroll
+                                for (int q = 0; q < 9; ++q) {
+                                    const uint32_t srcw = q < 4 ? A0 : (q < 8 ? A1 : A2);
+                                    const float pv = __uint_as_float(prmt(srcw, 0x4B000000u, 0x7440u | (uint32_t)(q & 3))) - 8388608.0f;
+                                    dW[ky * 9 + q] = fmaf(g, pv, dW[ky * 9 + q]);
+                                }
+                            }
+                        }
+                    }
+                    ccol[j] = ncol;
+                    la = a[CW - 1];
+                    lb = b[CW - 1];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fr_empty[buf]);  // this warp is done gathering from the frame
+        }
+        if (cur_cb >= 0) flush(cur_cb);
+        for (int cb = 0; cb < p.ncb; ++cb)  // channel blocks this CTA never worked on: their slots must still hold zeros
+            if (!(flushed & (1u << cb))) flush(cb);
     } else {
         // ================= epilogue (warps 0..7): thread = output channel; pooling in registers =================
         using OutT = typename std::conditional<F32OUT, float, __nv_bfloat16>::type;
@@ -418,8 +558,8 @@ static bool firstconv_tc_applies(int H, int W) {
     return g_fc_mode == 1 && (W == 32 || W == 64 || W == 128) && (long long)H * W * 3 <= kFtMaxFrameBytes && H % 2 == 0;
 }
 
-template <int W, bool F32OUT>
-static int launch_firstconv_tc(const FirstconvTcParams& p0, void* stream) {
+template <int W, bool F32OUT, bool BWD = false>
+static int launch_firstconv_tc(const FirstconvTcParams& p0, void* stream, int fixed_grid = 0) {
     FirstconvTcParams p = p0;
     const int pitch = W * 3;
     p.frame_stride = ((p.H * pitch + 48) + 15) / 16 * 16;
@@ -432,12 +572,13 @@ static int launch_firstconv_tc(const FirstconvTcParams& p0, void* stream) {
     const size_t smem = fixed + bst * bstage;
     static size_t attr = 0;
     if (smem > attr) {
-        VPT_CUDA(cudaFuncSetAttribute(firstconv_tc_kernel<W, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VPT_CUDA(cudaFuncSetAttribute(firstconv_tc_kernel<W, F32OUT, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     long long grid = num_sms() > 0 ? num_sms() : 148;
     if (grid > p.items) grid = p.items;
-    firstconv_tc_kernel<W, F32OUT><<<(unsigned)grid, kFtThreads, smem, (cudaStream_t)stream>>>(p);
+    if (fixed_grid > 0) grid = fixed_grid;  // backward: the partial-sum workspace is sized for exactly this many CTAs
+    firstconv_tc_kernel<W, F32OUT, BWD><<<(unsigned)grid, kFtThreads, smem, (cudaStream_t)stream>>>(p);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
