@@ -103,8 +103,10 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 
 // chan_part (optional, needs 256 % C8 == 0 so that a thread keeps one channel group): float2 [F][gridDim.x][C] per-CHANNEL (sum, sumsq)
 // partials of the pooled values -- what the two-norm composition (vpt_norm2_fold) needs instead of a normalisation pass.
+// (CHAN keeps 16 more accumulators: 48 registers -> 5 resident blocks instead of 8, and this kernel lives on loads in flight; two
+//  items per trip and a 4-block bound give each thread twice the loads instead -- measured in profiles/fold_r2.md)
 template <bool CHAN>
-__global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+__global__ void __launch_bounds__(256, CHAN ? 4 : 8) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                            float2* __restrict__ stat_part, float2* __restrict__ chan_part, int H, int W, int C8, int zp) {
     const int Ho = H >> 1, Wo = W >> 1;
     const int ipitch = W + zp, opitch = Wo + zp;  // ZP layout: one extra zero column (and row) per frame
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const uint4* __restrict
     float cs[8], css[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) cs[j] = css[j] = 0.f;
+#pragma unroll(CHAN ? 2 : 1)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
         const int c = i % C8, px = (i / C8) % opitch, py = i / (C8 * opitch);
         uint4 m = make_uint4(0, 0, 0, 0);  // inputs are >= 0 (post-ReLU), so 0 == -inf padding
