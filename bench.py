@@ -240,7 +240,7 @@ def gpu_eager_baseline(width, dev, B=4, T=128, seconds=6.0):
     return out
 
 
-def sample_agreement(pol, kw, dev, B=2, T=24, seed=1234):
+def sample_agreement(pol, kw, dev, B=2, T=64, seed=1234):
     """End-to-end agreement of the SAMPLED action indices with the oracle (north_star: 'bit-exact on sampled action indices under a
     fixed seed'; lib/action_head.py:195-207): the CUDA policy (bf16 operands) and the fp32 oracle (host CPU) see the same frames, the
     same weights and the same uniforms (the CUDA Philox stream after torch.manual_seed(seed), drawn camera-then-buttons like
