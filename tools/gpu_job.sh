@@ -1,9 +1,12 @@
 #!/bin/bash
+# One gpurun call = one batch of GPU work (this is the script the builder edits between calls; it travels with the repo snapshot).
 mkdir -p gpurun_out
-echo "=== 1x by shape"; timeout 600 python bench.py --width 1x --batch 64 --steps 5 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/bench_1x.json 2> gpurun_out/bench_1x.err; python - <<'PY'
+echo "=== full gpu tests"; timeout 1800 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+echo "=== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+echo "=== bench.py (all extras)"; timeout 1200 python bench.py > gpurun_out/bench_r2h.json 2> gpurun_out/bench_r2h.err; python - <<'PY'
 import json
-d=json.load(open("gpurun_out/bench_1x.json"))
-print("ms/step", d["ms_per_step"], "fps", d["value"], "frac", d["roofline"]["frac"], "whole", d["roofline"]["whole_step_frac_of_flop_roofline"], "kernel ms", d["roofline"]["kernel_ms_per_step"])
-for r in d["roofline"]["by_shape"][:8]: print(r)
+d=json.load(open("gpurun_out/bench_r2h.json"))
+print("ms/step", d["ms_per_step"], "fps", d["value"], "e2e", d["e2e"]["value"], "frac", d["roofline"]["frac"], "whole", d["roofline"]["whole_step_frac_of_flop_roofline"], "clk", d["clocks"], "launches", d["gpu_launches"])
+for k in ("sample_agreement","gpu_eager_baseline","configs","bc"): print(k, json.dumps(d[k])[:600])
 PY
-echo "=== 1x launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 320 --csv --log-file gpurun_out/launches_1x.csv python bench.py --width 1x --batch 64 --steps 2 --warmup 1 --no-extras --no-cpu-baseline > /dev/null 2>&1; python tools/summarize_launches.py gpurun_out/launches_1x.csv | head -16
+tail -3 gpurun_out/bench_r2h.err
