@@ -264,14 +264,25 @@ def sample_agreement(pol, kw, dev, B=2, T=64, seed=1234):
     with torch.no_grad():
         (pd_o, _, _), _ = O.agent_policy_forward(sd, cfg, img, first, O.initial_state(cfg, B))
     torch.set_num_threads(nthr)
+    # the same in the fp32-parity mode (precise.py): the mode in which "bit-exact sampled indices" is a meaningful target
+    pol.set_precision("fp32")
+    try:
+        (pd32, _, _), _ = pol({"img": img.to(dev)}, first.to(dev), pol.initial_state(B))
+        torch.manual_seed(seed)
+        ac32 = pol.sample(pd32)
+        ac32_det = pol.sample(pd32, deterministic=True)
+    finally:
+        pol.set_precision("bf16")
     out = {"frames": B * T, "seed": seed, "rng": "CUDA Philox, torch.manual_seed(seed), camera then buttons"}
     for name in pd:
         so = O.gumbel_sample(pd_o[name], us[name])
         do = torch.argmax(pd_o[name], dim=-1)
         n = so.numel()
-        out[name] = {"stochastic_agree": int((ac[name].cpu().view_as(so) == so).sum()) / n,
-                     "deterministic_agree": int((ac_det[name].cpu().view_as(do) == do).sum()) / n,
-                     "logprob_max_rel_err": float(((pd[name].cpu() - pd_o[name]).abs() / pd_o[name].abs()).max())}
+        agree = lambda a, ref: int((a.cpu().view_as(ref) == ref).sum()) / n
+        out[name] = {"stochastic_agree": agree(ac[name], so), "deterministic_agree": agree(ac_det[name], do),
+                     "logprob_max_rel_err": float(((pd[name].cpu() - pd_o[name]).abs() / pd_o[name].abs()).max()),
+                     "fp32_mode": {"stochastic_agree": agree(ac32[name], so), "deterministic_agree": agree(ac32_det[name], do),
+                                   "logprob_max_rel_err": float(((pd32[name].cpu() - pd_o[name]).abs() / pd_o[name].abs()).max())}}
     return out
 
 

@@ -256,6 +256,10 @@ int vpt_stats_finalize(const float* stat_part, float* mr, int64_t G, int32_t n_p
 int vpt_copy_rows(const void* src, int32_t src_f32, int64_t src_bstride, int64_t src_ld, int64_t src_off, void* dst,
                   int32_t dst_f32, int64_t dst_bstride, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t rows,
                   int32_t cols, void* stream);
+/* Same for TWO (source, destination) pairs of identical geometry in one launch (the K and the V memory of a layer). */
+int vpt_copy_rows2(const void* src, const void* src2, int32_t src_f32, int64_t src_bstride, int64_t src_ld, int64_t src_off, void* dst,
+                   void* dst2, int32_t dst_f32, int64_t dst_bstride, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t rows, int32_t cols,
+                   void* stream);
 
 /* new_mask[b][j] = j < maxlen - min(t,maxlen) ? (mask[b][j + t] && !first[b]) : 1   (lib/masked_attention.py:86-92)
  * mask_in may be NULL (= all zero, the state after initial_state()).  u8 0/1 arrays. */

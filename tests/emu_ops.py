@@ -293,6 +293,11 @@ def copy_rows(src, src_off, dst, dst_off, rows):
         dst[:, dst_off:dst_off + rows] = src[:, src_off:src_off + rows].to(dst.dtype)
 
 
+def copy_rows2(src_a, src_b, src_off, dst_a, dst_b, dst_off, rows):
+    copy_rows(src_a, src_off, dst_a, dst_off, rows)
+    copy_rows(src_b, src_off, dst_b, dst_off, rows)
+
+
 def state_mask_update(mask_in, first_u8, t, maxlen):
     B = first_u8.shape[0]
     if mask_in is None:

@@ -319,7 +319,7 @@ def test_gemm_column_segments_fused_qkvr():
     """vpt_gemm_args.dst_*: ONE GEMM over the concatenated Q | K | V | R weight writes each column segment to its own destination
     (bf16 q; K / V into the rows after the memory of the [B][maxlen + t][h] buffers through the row remap; R in fp32) == four GEMMs."""
     g = torch.Generator().manual_seed(31)
-    for (B, t, maxlen, h, heads) in [(3, 8, 16, 256, 2), (2, 128, 128, 1024, 8)]:
+    for (B, t, maxlen, h, heads) in [(3, 8, 16, 256, 2), (2, 128, 128, 1024, 8), (1, 1, 16, 256, 2), (4, 2, 128, 1024, 8)]:  # last two: the small-M weight-streaming kernel
         M, T, nr = B * t, maxlen + t, 10 * heads
         x = _rand((M, h), g)
         Wc = _rand((3 * h + nr, h), g, h ** -0.5)

@@ -108,6 +108,7 @@ SIGNATURES = {
     "vpt_norm_stat_parts": (_I, [_I, _I]),
     "vpt_stats_finalize": (_I, [_P, _P, _L, _I, _D, _F, _P]),
     "vpt_copy_rows": (_I, [_P, _I, _L, _L, _L, _P, _I, _L, _L, _L, _I, _I, _I, _P]),
+    "vpt_copy_rows2": (_I, [_P, _P, _I, _L, _L, _L, _P, _P, _I, _L, _L, _L, _I, _I, _I, _P]),
     "vpt_state_mask_update": (_I, [_P, _P, _L, _P, _I, _I, _I, _P]),
     "vpt_attention": (_I, [_P, _P, _P, _P, _L, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vpt_log_softmax": (_I, [_P, _L, _I, _I, _P, _L, _P]),

@@ -411,9 +411,12 @@ __global__ void __launch_bounds__(256) affine_norm_zp_rows_kernel(const uint4* _
 // strided row copy with fp32 <-> bf16 conversion (KV memory load/store); 8 elements per thread
 // ---------------------------------------------------------------------------------------------------------
 template <bool SRC_F32, bool DST_F32>
-__global__ void __launch_bounds__(256) copy_rows_kernel(const void* __restrict__ src, long long src_bstride, long long src_ld,
-                                                          long long src_off, void* __restrict__ dst, long long dst_bstride,
-                                                          long long dst_ld, long long dst_off, int rows, int cols8) {
+__global__ void __launch_bounds__(256) copy_rows_kernel(const void* __restrict__ src0, const void* __restrict__ src1, long long src_bstride,
+                                                          long long src_ld, long long src_off, void* __restrict__ dst0, void* __restrict__ dst1,
+                                                          long long dst_bstride, long long dst_ld, long long dst_off, int rows, int cols8) {
+    // blockIdx.z selects one of two (source, destination) pairs of identical geometry (K and V of a layer in one launch)
+    const void* src = blockIdx.z ? src1 : src0;
+    void* dst = blockIdx.z ? dst1 : dst0;
     const int b = blockIdx.y;
     const long long n = (long long)rows * cols8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -572,19 +575,29 @@ extern "C" int vpt_affine_norm_zp(const void* in, const float* mr, const float* 
     return VPT_OK;
 }
 
+extern "C" int vpt_copy_rows2(const void* src, const void* src2, int32_t src_f32, int64_t src_bstride, int64_t src_ld, int64_t src_off, void* dst,
+                              void* dst2, int32_t dst_f32, int64_t dst_bstride, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t rows,
+                              int32_t cols, void* stream);
+
 extern "C" int vpt_copy_rows(const void* src, int32_t src_f32, int64_t src_bstride, int64_t src_ld, int64_t src_off, void* dst,
                              int32_t dst_f32, int64_t dst_bstride, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t rows,
                              int32_t cols, void* stream) {
+    return vpt_copy_rows2(src, nullptr, src_f32, src_bstride, src_ld, src_off, dst, nullptr, dst_f32, dst_bstride, dst_ld, dst_off, B, rows, cols, stream);
+}
+
+extern "C" int vpt_copy_rows2(const void* src, const void* src2, int32_t src_f32, int64_t src_bstride, int64_t src_ld, int64_t src_off, void* dst,
+                              void* dst2, int32_t dst_f32, int64_t dst_bstride, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t rows,
+                              int32_t cols, void* stream) {
     using namespace vpt;
     if (rows == 0 || B == 0) return VPT_OK;
-    VPT_CHECK(src && dst && B > 0 && rows > 0 && cols > 0, "vpt_copy_rows: bad arguments");
+    VPT_CHECK(src && dst && B > 0 && rows > 0 && cols > 0 && (!src2 == !dst2), "vpt_copy_rows: bad arguments");
     VPT_CHECK(cols % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0 && src_bstride % 8 == 0 && dst_bstride % 8 == 0,
               "vpt_copy_rows: cols / pitches must be multiples of 8");
     VPT_CHECK(B <= 65535, "vpt_copy_rows: B too large");
-    dim3 grid(vpt_blocks_for((long long)rows * (cols / 8), 1024, 1024), B);
+    dim3 grid(vpt_blocks_for((long long)rows * (cols / 8), 1024, 1024), B, src2 ? 2 : 1);
     cudaStream_t s = (cudaStream_t)stream;
-#define VPT_CR(SF, DF)                                                                                                        \
-    copy_rows_kernel<SF, DF><<<grid, 256, 0, s>>>(src, src_bstride, src_ld, src_off, dst, dst_bstride, dst_ld, dst_off, rows, \
+#define VPT_CR(SF, DF)                                                                                                                        \
+    copy_rows_kernel<SF, DF><<<grid, 256, 0, s>>>(src, src2, src_bstride, src_ld, src_off, dst, dst2, dst_bstride, dst_ld, dst_off, rows, \
                                                   cols / 8)
     if (src_f32 && dst_f32) VPT_CR(true, true);
     else if (src_f32) VPT_CR(true, false);

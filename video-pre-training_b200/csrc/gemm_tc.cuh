@@ -515,7 +515,7 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     VPT_CHECK(a->mr == nullptr || a->rows_per_group > 0, "vpt_gemm_bf16: rows_per_group must be > 0 with mr");
     VPT_CHECK(a->stat_part == nullptr || a->stat_mode == 1 || a->stat_mode == 2, "vpt_gemm_bf16: bad stat_mode %d", a->stat_mode);
     VPT_CHECK(!(a->mr && !a->S1), "vpt_gemm_bf16: mr given without S1");
-    if (g_small_m_enabled && a->ndst == 0) {  // rollout path: a handful of rows -> weight-streaming kernel (csrc/gemv_small.cuh)
+    if (g_small_m_enabled) {  // rollout path: a handful of rows -> weight-streaming kernel (csrc/gemv_small.cuh)
         const int r = try_launch_gemv_small_fwd(a, stream);
         if (r <= 0) return r;
     }

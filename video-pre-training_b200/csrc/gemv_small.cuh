@@ -58,10 +58,22 @@ __global__ void __launch_bounds__(kGsThreads) gemv_small_kernel(const __nv_bfloa
                 }
                 if (p.relu == 2) v = fmaxf(v, 0.f);
                 v *= p.out_scale;
+                // destination: the single one, or the column segment n falls into (fused projections, vpt_gemm_args.dst_*)
+                void* d_out = p.out;
+                long long d_ld = p.ld_out;
+                int d_f32 = p.out_f32, d_col0 = 0;
+                bool d_remap = p.seg_len > 0;
+                if (p.ndst > 0) {
+                    int sg = 0;
+                    for (int i = 1; i < p.ndst; ++i)
+                        if (n >= p.dst_n0[i]) sg = i;
+                    d_out = p.dst_out[sg]; d_ld = p.dst_ld[sg]; d_f32 = p.dst_f32[sg]; d_col0 = p.dst_n0[sg];
+                    d_remap = d_remap && p.dst_remap[sg] != 0;
+                }
                 long long orow = m;
-                if (p.seg_len > 0) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
-                if (p.out_f32) reinterpret_cast<float*>(p.out)[(size_t)orow * p.ld_out + n] = v;
-                else reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)orow * p.ld_out + n] = __float2bfloat16_rn(v);
+                if (d_remap) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
+                if (d_f32) reinterpret_cast<float*>(d_out)[(size_t)orow * d_ld + (n - d_col0)] = v;
+                else reinterpret_cast<__nv_bfloat16*>(d_out)[(size_t)orow * d_ld + (n - d_col0)] = __float2bfloat16_rn(v);
             }
         }
     }
@@ -88,7 +100,7 @@ __global__ void __launch_bounds__(256) row_stats_small_kernel(const GemmParams p
 
 // returns VPT_OK after launching, or 1 if this shape is not handled here (caller falls through to the tensor-core kernel)
 static int try_launch_gemv_small(const vpt_gemm_args* a, void* stream) {
-    if (a->conv || a->M > kGsMaxM || (a->K & 7) != 0 || (a->stat_part && a->stat_mode != 1)) return 1;
+    if (a->conv || a->M > kGsMaxM || (a->K & 7) != 0 || (a->stat_part && a->stat_mode != 1) || (a->ndst > 0 && a->stat_part)) return 1;
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = a->M; p.N = a->N; p.K = a->K;
@@ -99,6 +111,10 @@ static int try_launch_gemv_small(const vpt_gemm_args* a, void* stream) {
     p.out = a->out; p.out_f32 = a->out_f32; p.ld_out = a->ld_out;
     p.seg_len = a->seg_len; p.seg_stride = a->seg_stride; p.seg_off = a->seg_off;
     p.stat_part = a->stat_part; p.stat_mode = a->stat_mode;
+    p.ndst = a->ndst;
+    for (int i = 0; i < a->ndst && i < 4; ++i) {
+        p.dst_n0[i] = a->dst_n0[i]; p.dst_out[i] = a->dst_out[i]; p.dst_ld[i] = a->dst_ld[i]; p.dst_f32[i] = a->dst_f32[i]; p.dst_remap[i] = a->dst_remap[i];
+    }
     int bn, nt;
     choose_block_n(a->N, &bn, &nt);
     const int P = nt * 2;  // == vpt_gemm_stat_parts(N)

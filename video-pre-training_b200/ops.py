@@ -287,6 +287,19 @@ def copy_rows(src, src_off, dst, dst_off, rows):
     _count()
 
 
+def copy_rows2(src_a, src_b, src_off, dst_a, dst_b, dst_off, rows):
+    """copy_rows for two (source, destination) pairs of identical shape / strides / dtypes in ONE launch (K and V of a layer)."""
+    _cuda(src_a, src_b, dst_a, dst_b)
+    if rows == 0:
+        return
+    assert src_a.shape == src_b.shape and src_a.stride() == src_b.stride() and src_a.dtype == src_b.dtype
+    assert dst_a.shape == dst_b.shape and dst_a.stride() == dst_b.stride() and dst_a.dtype == dst_b.dtype
+    B, _, Cc = src_a.shape
+    nat.check(nat.lib().vpt_copy_rows2(_p(src_a), _p(src_b), int(src_a.dtype == F32), src_a.stride(0), src_a.stride(1), src_off, _p(dst_a), _p(dst_b),
+                                       int(dst_a.dtype == F32), dst_a.stride(0), dst_a.stride(1), dst_off, B, rows, Cc, _stream()), "vpt_copy_rows2")
+    _count()
+
+
 def state_mask_update(mask_in, first_u8, t, maxlen):
     """mask_in: bool (B,1,maxlen) or None; first_u8: u8 view of first (B,T); returns new bool (B,1,maxlen)."""
     B = first_u8.shape[0]

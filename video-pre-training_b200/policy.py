@@ -486,10 +486,13 @@ class MinecraftPolicy(nn.Module):
         if maxlen > 0:
             if mem_k.shape != (B, maxlen, h):
                 raise AssertionError(f"KV memory shape {tuple(mem_k.shape)} != {(B, maxlen, h)}")
-            ops.copy_rows(mem_k, 0, full_k, 0, maxlen)  # lib/xf.py:378-379  full = cat(prev, new)
-            ops.copy_rows(mem_v, 0, full_v, 0, maxlen)
+            if mem_k.stride() == mem_v.stride() and mem_k.dtype == mem_v.dtype:
+                ops.copy_rows2(mem_k, mem_v, 0, full_k, full_v, 0, maxlen)  # lib/xf.py:378-379  full = cat(prev, new), K and V in one launch
+            else:
+                ops.copy_rows(mem_k, 0, full_k, 0, maxlen)
+                ops.copy_rows(mem_v, 0, full_v, 0, maxlen)
         R = None
-        if B * t > 8 and h % 256 == 0:
+        if h % 256 == 0:
             # Q | K | V | R as ONE GEMM: K / V land in the rows of `full` after the memory (row remap), R in fp32
             q = torch.empty((B * t, h), dtype=BF16, device=x.device)
             dsts = [(0, q, h, False), (h, full_k, h, True), (2 * h, full_v, h, True)]
@@ -498,7 +501,7 @@ class MinecraftPolicy(nn.Module):
                 dsts.append((3 * h, R, NBASIS * heads, False))
             Wc, _, bc = L["qkvr"]
             ops.gemm(xhat, Wc, q, B * t, Wc.shape[0], h, S2=bc, seg=(t, T, maxlen), dsts=dsts)
-        else:  # a handful of rows (rollout): four weight-streaming launches (csrc/gemv_small.cuh)
+        else:  # hidsize not a multiple of the N tile: four launches
             q, _ = self._linear(xhat, L["q"], h)
             self._linear(xhat, L["k"], h, out=full_k, seg=(t, T, maxlen), ld_out=h)
             self._linear(xhat, L["v"], h, out=full_v, seg=(t, T, maxlen), ld_out=h)
@@ -509,8 +512,7 @@ class MinecraftPolicy(nn.Module):
         # new state (lib/xf.py:380-381: last `maxlen` rows of full; lib/masked_attention.py:86-92)
         new_k = torch.empty((B, maxlen, h), dtype=F32, device=x.device)
         new_v = torch.empty((B, maxlen, h), dtype=F32, device=x.device)
-        ops.copy_rows(full_k, T - maxlen, new_k, 0, maxlen)
-        ops.copy_rows(full_v, T - maxlen, new_v, 0, maxlen)
+        ops.copy_rows2(full_k, full_v, T - maxlen, new_k, new_v, 0, maxlen)
         new_mask = ops.state_mask_update(smask_u8, first_u8, t, maxlen) if causal else state_mask
         y, mr_y = self._linear(a, L["proj"], h, residual=xhat, want_stats=True)
         self._tap(f"recurrent_layer.blocks.{l}.attn", y)
@@ -915,8 +917,8 @@ class GraphedAct:
             ac, st, res = self.policy.act({"img": self.img}, self.first, self.state, stochastic=stochastic, return_pd=True)
             for (m_in, (k_in, v_in)), (m_out, (k_out, v_out)) in zip(self.state, st):  # roll the state inside the graph
                 m_in.copy_(m_out)
-                k_in.copy_(k_out)
-                v_in.copy_(v_out)
+                if k_in.shape[1] > 0:
+                    ops.copy_rows2(k_out, v_out, 0, k_in, v_in, 0, k_in.shape[1])  # K and V in one launch
         self.graphs[stochastic] = (g, ac, res)
         return self.graphs[stochastic]
 
