@@ -140,7 +140,8 @@ def test_conv3x3_zp(H, W, Cin, Cout, F_):
     try:
         # pair: one CTA per tile / SM pairs with tcgen05.mma.cta_group::2; swap: operand-swapped kernel for Cout == 128
         # swap 4: the experimental fragment epilogue (tcgen05.ld.16x256b -> stmatrix.trans -> TMA store; falls back below 256 rows / frame)
-        for pair, swap in ((0, 0), (2, 0), (0, 1), (0, 4)) if Cout == 128 else ((0, 0), (2, 0), (0x100, 0), (0x102, 0)):
+        # swap 5: channel-major single-pass epilogue (lane-pair exchange -> bf16 staging -> TMA store; same fallback)
+        for pair, swap in ((0, 0), (2, 0), (0, 1), (0, 4), (0, 5)) if Cout == 128 else ((0, 0), (2, 0), (0x100, 0), (0x102, 0)):
             nat.lib().vpt_set_conv_pair_mode(pair)
             nat.lib().vpt_set_conv_swap_mode(swap)
             for residual in (None, res):
@@ -371,7 +372,7 @@ def test_two_norm_composition_kernels():
         _close(f"norm2_fold {name}", a, r, rtol=1e-4, atol=1e-4)
     # conv epilogues with a per-frame table and an affine residual
     try:
-        for (H, W, Cin, Cout, F_, modes) in [(16, 16, 128, 256, 3, ((1, 1), (0x101, 1), (0, 1))), (32, 32, 128, 128, 2, ((1, 1), (1, 0))),
+        for (H, W, Cin, Cout, F_, modes) in [(16, 16, 128, 256, 3, ((1, 1), (0x101, 1), (0, 1))), (32, 32, 128, 128, 2, ((1, 1), (1, 5), (1, 0))), (64, 64, 128, 128, 3, ((1, 1), (1, 5))),
                                              (8, 8, 64, 64, 5, ((1, 1),))]:
             x = E.to_zp(_rand((F_, H, W, Cin), g))
             Wb = _rand((Cout, 9 * Cin), g, (9 * Cin) ** -0.5)

@@ -1,4 +1,6 @@
-"""Micro-benchmark of vpt_conv3x3_zp over the 2x-width layer shapes: A/B of the epilogue variants.
+"""Micro-benchmark of vpt_conv3x3_zp on the stack-0 layer shape (128 -> 128 @ 64x64): A/B of the Cout == 128 kernel's epilogue variants.
+  swap mode 1 = two-phase transposing epilogue (default), 2 = no epilogue (MMA-rate experiment), 4 = fragment epilogue, 5 = channel-major
+  single-pass epilogue (v3); bits 8..15 cap the weight pipeline depth, bits 20..23 switch parts of v3 off (timing experiments only).
   pair mode bit 8 (0x100) = round-1 per-thread global-store epilogue instead of the TMA-store one (pair kernel)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,9 +9,8 @@ import vpt_b200
 from video_pre_training_b200 import _native as nat, ops
 l = nat.lib()
 g = torch.Generator().manual_seed(0)
-shapes = [(64, 128, 256, 2048, False), (32, 256, 256, 2048, False), (32, 256, 256, 2048, True), (16, 256, 256, 2048, True),
-          (64, 128, 128, 2048, True)]
-variants = [("tma-epi/2phase", 1, 1), ("r1-epi/frag", 0x101, 4)]
+shapes = [(64, 128, 128, 2048, False), (64, 128, 128, 2048, True)]
+variants = [("2phase", 1, 1), ("mma-only", 1, 2), ("frag", 1, 4), ("v3", 1, 5), ("v3 -class", 1, 0x200005)]
 for (HW, Cin, N, F_, res) in shapes:
     x = torch.zeros(F_, HW + 1, HW + 1, Cin, dtype=torch.bfloat16, device="cuda")
     x[:, :HW, :HW] = torch.randn(F_, HW, HW, Cin, device="cuda").to(torch.bfloat16)
@@ -31,7 +32,7 @@ for (HW, Cin, N, F_, res) in shapes:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            out, _ = ops.conv3x3_zp(x, Wb, HW, HW, mr=mr, S1=S1, S2=S2, relu=1, residual=r, want_stats=False)
+            out, _ = ops.conv3x3_zp(x, Wb, HW, HW, mr=mr, S1=S1, S2=S2, relu=1, residual=r, want_stats=True)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         nat.device_check()

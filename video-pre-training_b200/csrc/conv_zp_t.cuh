@@ -66,6 +66,18 @@ __device__ __forceinline__ float transpose_reduce32(float (&x)[32], int lane) {
     return x[0];
 }
 
+// epilogue v3 helpers: patch / zero ONE compile-time element of the chunk (used under a jump table on a warp-uniform position)
+template <int J>
+__device__ __forceinline__ void v3_patch(float (&x)[32], const uint32_t (&acc)[32], float ga, float e) {
+    if constexpr (J >= 0 && J < 32) x[J] = fmaf(ga, __uint_as_float(acc[J]), e);
+}
+template <int J>
+__device__ __forceinline__ void v3_zero(float (&x)[32]) {
+    if constexpr (J >= 0 && J < 32) x[J] = 0.f;
+}
+#define VPT_V3_CASES(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16) M(17) M(18) M(19) M(20) \
+    M(21) M(22) M(23) M(24) M(25) M(26) M(27) M(28) M(29) M(30) M(31) M(32) M(33)
+
 // kFold (compile time, so that the plain variant's epilogue -- the co-bottleneck of this kernel -- is untouched by the extra code):
 // 0 = plain (S1 / S2 class tables), 1 = per-frame fold table Ef, 2 = plain fold + affine residual (two-norm composition, vpt_norm2_fold)
 template <int kFold>
@@ -79,7 +91,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint8_t* smem_x = smem;                                 // 2 activation-span stages
     uint8_t* smem_w = smem + 2 * (size_t)p.a_stage_bytes;   // weight tiles
     uint8_t* smem_stage = smem + p.stage_off;               // epi_mode 1: 4 boxes [128 pixels][64 channels] bf16, SWIZZLE_128B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + (size_t)p.b_stages * w_stage_bytes + (p.epi_mode == 1 ? 65536 : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + (size_t)p.b_stages * w_stage_bytes + (p.epi_mode != 0 ? 65536 : 0));
     uint64_t* x_full = bars;
     uint64_t* x_empty = bars + 2;
     uint64_t* w_full = bars + 4;
@@ -98,9 +110,9 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
-        if (p.epi_mode == 1) {
+        if (p.epi_mode != 0) {
             tma_prefetch_desc(&tmO);
-            if (p.residual) tma_prefetch_desc(&tmR);
+            if (p.residual && p.epi_mode == 1) tma_prefetch_desc(&tmR);
         }
         for (int i = 0; i < 4; ++i) mbar_init(&slot_ready[i], 1);
         for (int i = 0; i < 2; ++i) {
@@ -355,6 +367,237 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
         }
         if (leader_t) bulk_wait_all<0>();
+    } else if (p.epi_mode == 2) {
+        // ================= epilogue v3 (warps 3..10): channel-major single pass -> bf16 staging -> TMA store =================
+        // Thread = output channel (its TMEM lane), warp = 32 channels x one 128-pixel half.  Everything that depends on the PIXEL
+        // (frame statistics, border class, zero row / column) is warp-uniform in this layout, so the fold is one FFMA per value with
+        // per-channel constants in registers; the rare non-interior pixels are patched under uniform branches.  The 32 values of a
+        // chunk are processed as straight-line passes (the first version interleaved the per-pixel branches with the arithmetic
+        // and was latency bound at 2 warps per scheduler: 4.7 ms instead of 2.1).  Values are rounded to bf16 in registers;
+        // neighbouring lanes (channels 2i, 2i+1) exchange one packed pair per two pixels so that each lane owns a 32-bit (channel pair)
+        // word, stored into a [pixel][64 channels] SWIZZLE_128B box handed to TMA (UTMASTG) in two 64-pixel halves: the first half's
+        // store overlaps the second half's arithmetic and nobody ever waits for a store issued less than half a tile ago.
+        // Lane 2i takes pixel j, lane 2i+1 pixel j+4: the two 64-byte row segments land in disjoint banks (XOR swizzle flips chunk
+        // bit 2).  The residual comes straight from global memory in the same (channel pair) word layout, one chunk ahead.
+        // Shared-memory traffic per tile: 64 KB written + 64 KB read by TMA instead of the 128 KB fp32 transposed tile written and
+        // re-read, and no LSU global stores.
+        const int ew = warp - 3;
+        const int quarter = warp & 3;        // TMEM lane quarter = channels [32 quarter, +32)
+        const int g = ew >> 2;               // pixel half of the tile: columns [128 g, +128)
+        const int ch = quarter * 32 + lane;
+        const int box = (quarter >> 1) * 2 + g;  // staging box: channels [64 (quarter/2), +64) x this half's 128 pixels
+        uint8_t* stg = smem_stage + (size_t)box * 16384;
+        const bool leader_t = ((quarter & 1) == 0) && lane == 0;
+        const int odd = lane & 1, pi = lane >> 1;
+        // byte offset of this lane's word inside row (8 m' + k) [+4 for odd lanes] of the box, k = 0..3
+        const uint32_t cl = (uint32_t)((quarter & 1) * 4 + (pi >> 2)) ^ (uint32_t)(odd << 2);
+        uint32_t off[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) off[k] = smem_u32(stg) + (uint32_t)odd * 512u + (uint32_t)k * 128u + ((cl ^ (uint32_t)k) << 4) + (uint32_t)(pi & 3) * 4u;
+        const uint32_t* res_w = reinterpret_cast<const uint32_t*>(p.residual) + (quarter * 16 + pi);  // this lane's channel pair, [pixel] stride 64 words
+        // fold-table entries of the three classes an ordinary row has: 3 (x = 0), 4 (interior), 5 (x = W - 1)
+        float s1k[3], s2k[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s1k[k] = (kFold != 1 && p.S1) ? __ldg(p.S1 + (3 + k) * 128 + ch) : 0.f;
+            s2k[k] = (kFold != 1 && p.S2) ? __ldg(p.S2 + (3 + k) * 128 + ch) : 0.f;
+        }
+        // frame state (warp-uniform) and this channel's constants for it
+        unsigned fcur = 0xffffffffu;
+        float ga = 1.f, gb = 0.f, eI = 0.f, e3 = 0.f, e5 = 0.f, raI = 1.f, rbI = 0.f;
+        auto load_frame = [&](unsigned f) {
+            fcur = f;
+            if (p.mr) {
+                const float mean = __ldg(p.mr + 2 * (size_t)f), rstd = __ldg(p.mr + 2 * (size_t)f + 1);
+                ga = rstd;
+                gb = rstd * mean;
+            }
+            if (kFold == 1) {
+                const float* e = p.Ef + ((size_t)f * 9 + 3) * 128 + ch;
+                e3 = __ldg(e); eI = __ldg(e + 128); e5 = __ldg(e + 256);
+            } else {
+                e3 = fmaf(-gb, s1k[0], s2k[0]); eI = fmaf(-gb, s1k[1], s2k[1]); e5 = fmaf(-gb, s1k[2], s2k[2]);
+            }
+            if (kFold == 2) {
+                raI = __ldg(p.res_scale + (size_t)f * 128 + ch);
+                rbI = __ldg(p.res_shift + (size_t)f * 128 + ch);
+            }
+        };
+        uint32_t rw_next[16];  // residual words of the NEXT chunk (pixel pairs (ja, ja + 4): even lanes hold pixel ja, odd lanes pixel jb)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rw_next[i] = 0u;
+        auto prefetch_res = [&](long long qc) {  // chunk starting at ZP pixel qc
+            if (!p.residual) return;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const long long q = qc + (i >> 2) * 8 + (i & 3) + 4 * odd;
+                rw_next[i] = q < p.Q ? __ldg(res_w + (size_t)q * 64) : 0u;
+            }
+        };
+        if ((long long)blockIdx.x < p.num_tiles) prefetch_res((long long)blockIdx.x * kCtPix + 128 * g);
+        int local = 0;
+        bool ok = true;
+        for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const uint32_t accphase = (uint32_t)(local >> 1) & 1u;
+            const long long qh = tile * kCtPix + 128 * g;
+            const unsigned fA = (unsigned)((tile * kCtPix) / p.FS);  // first frame this tile touches (the other one, if any, is fA + 1)
+            const unsigned fh = qh < p.Q ? (unsigned)(((qh + 31 < p.Q) ? qh + 31 : p.Q - 1) / p.FS) : fA;  // frame of the first chunk
+            if (fh != fcur) load_frame(fh);  // (before the accumulator wait: the loads overlap it)
+            float s0 = 0.f, ss0 = 0.f, s1v = 0.f, ss1v = 0.f;  // statistics of the tile's first / second frame
+            if (!(ok = mbar_wait(&tmem_full_bar[as], accphase, 0x810u))) break;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {  // 32-pixel chunks of the half
+                // Lane-parallel pixel classification: code 0..8 border class (4 = interior), -1 zero row / column, -2 past the tensor.
+                // Maps are >= 32 wide (host check), so the valid pixels of one chunk all belong to ONE frame: that of its last pixel
+                // (bottom row of a frame and top row of the next are W + 3 > 32 pixels apart).
+                const long long qc = qh + 32 * c;
+                int code_l = -2, x_l = 0;
+                bool plain_l = false;  // pixel of an ordinary row (1 <= y <= H - 2): classes 3 / 4 / 5 and the zero column only
+                {
+                    const long long q = qc + lane;
+                    if (q < p.Q) {
+                        const unsigned qq = (unsigned)q;
+                        const unsigned f_l = qq / (unsigned)p.FS;
+                        const unsigned r = qq - f_l * (unsigned)p.FS;
+                        const int y = (int)(r / (unsigned)p.Wp), x = (int)r - y * p.Wp;
+                        x_l = x;
+                        plain_l = y >= 1 && y <= p.H - 2;
+                        code_l = -1;
+                        if (y < p.H && x < p.W) code_l = ((y == 0) ? 0 : ((y == p.H - 1) ? 2 : 1)) * 3 + ((x == 0) ? 0 : ((x == p.W - 1) ? 2 : 1));
+                    }
+                }
+                unsigned special = __ballot_sync(0xffffffffu, code_l != 4);
+                unsigned zmask = __ballot_sync(0xffffffffu, code_l < 0);
+                // Ordinary rows (93 % of the chunks): the non-interior pixels are one (possibly cut) run x = W-1, W, 0 = class 5, zero, class 3
+                // at chunk positions jt, jt + 1, jt + 2 (W >= 33: the next run is out of the chunk); jsw = jt + 2 in [0, 33], 34 = none.
+                const bool plain = __ballot_sync(0xffffffffu, !plain_l) == 0u;
+                int jsw = 34;
+                if (plain) {
+                    const int x0 = __shfl_sync(0xffffffffu, x_l, 0);
+                    const int jt = x0 == 0 ? -2 : p.W - 1 - x0;  // (x0 == W: -1)
+                    jsw = jt + 2 < 34 ? jt + 2 : 34;
+                }
+                const long long qe = (qc + 31 < p.Q) ? qc + 31 : p.Q - 1;
+                unsigned fe = qc < p.Q ? (unsigned)(qe / p.FS) : fcur;
+                if (p.dbg_skip_epilogue & 32) { special = 0u; zmask = 0u; fe = fcur; jsw = 34; }
+                if (fe != fcur) load_frame(fe);
+                uint32_t rw[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rw[i] = rw_next[i];
+                {   // residual of the next chunk (of this tile, or the first one of this CTA's next tile)
+                    const long long tn = tile + gridDim.x;
+                    if (c < 3) prefetch_res(qc + 32);
+                    else if (tn < p.num_tiles) prefetch_res(tn * kCtPix + 128 * g);
+                }
+                uint32_t acc[32];
+                if (p.dbg_skip_epilogue & 128) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = (uint32_t)(j + c);
+                } else {
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + 128 * g + 32 * c), acc);
+                    tmem_ld_wait();
+                }
+                if (c == 3) {  // accumulator stage fully read
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                }
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = fmaf(ga, __uint_as_float(acc[j]), eI);
+                if (plain) {
+                    switch (jsw) {
+#define VPT_V3_PATCH(k) case k: v3_patch<k - 2>(x, acc, ga, e5); v3_patch<k>(x, acc, ga, e3); break;
+                        VPT_V3_CASES(VPT_V3_PATCH)
+#undef VPT_V3_PATCH
+                        default: break;
+                    }
+                } else if (special != 0u) {  // border rows / frame ends: per-pixel uniform branches (7 % of the chunks)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((special >> j) & 1u) {
+                            const int code = __shfl_sync(0xffffffffu, code_l, j);
+                            if (code >= 0) {
+                                float e;
+                                if (kFold == 1) e = __ldg(p.Ef + ((size_t)fcur * 9 + code) * 128 + ch);
+                                else e = fmaf(-gb, p.S1 ? __ldg(p.S1 + code * 128 + ch) : 0.f, p.S2 ? __ldg(p.S2 + code * 128 + ch) : 0.f);
+                                x[j] = fmaf(ga, __uint_as_float(acc[j]), e);
+                            }
+                        }
+                    }
+                }
+                if (p.relu == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (p.residual) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int ja = (i >> 2) * 8 + (i & 3), jb = ja + 4;
+                        const uint32_t w = rw[i];  // (even channel, odd channel) of pixel ja (even lanes) / jb (odd lanes)
+                        const uint32_t recv_r = __shfl_xor_sync(0xffffffffu, w, 1);
+                        // own channel: low half in even lanes, high half in odd lanes; pixel ja comes from the even lane's word
+                        const uint32_t wa = odd ? recv_r : w, wb = odd ? w : recv_r;
+                        const float ra = odd ? bf16_hi(wa) : bf16_lo(wa), rb = odd ? bf16_hi(wb) : bf16_lo(wb);
+                        x[ja] += (kFold == 2) ? fmaf(raI, ra, rbI) : ra;
+                        x[jb] += (kFold == 2) ? fmaf(raI, rb, rbI) : rb;
+                    }
+                }
+                if (p.relu == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (plain) {  // the zero column
+                    switch (jsw) {
+#define VPT_V3_ZERO(k) case k: v3_zero<k - 1>(x); break;
+                        VPT_V3_CASES(VPT_V3_ZERO)
+#undef VPT_V3_ZERO
+                        default: break;
+                    }
+                } else if (zmask != 0u) {  // zero row / column of the ZP layout (and rows past the tensor, which TMA clips)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = ((zmask >> j) & 1u) ? 0.f : x[j];
+                }
+                float cs[4] = {0.f, 0.f, 0.f, 0.f}, css[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int ja = (i >> 2) * 8 + (i & 3), jb = ja + 4;
+                    const uint32_t pk = pack_bf16(x[ja], x[jb]);  // own channel: (pixel ja, pixel jb), rounded
+                    const float lo = bf16_lo(pk), hi = bf16_hi(pk);
+                    cs[i & 3] += lo + hi;
+                    css[i & 3] = fmaf(lo, lo, fmaf(hi, hi, css[i & 3]));
+                    const uint32_t recv_o = __shfl_xor_sync(0xffffffffu, pk, 1);
+                    // even lane: word of pixel ja = (own ja, partner's ja); odd lane: word of pixel jb = (partner's jb, own jb)
+                    const uint32_t word = odd ? __byte_perm(recv_o, pk, 0x7632) : __byte_perm(pk, recv_o, 0x5410);
+                    if (!(p.dbg_skip_epilogue & 16))
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(off[i & 3] + (uint32_t)(c * 4096 + (i >> 2) * 1024)), "r"(word) : "memory");
+                }
+                {
+                    const float a = (cs[0] + cs[1]) + (cs[2] + cs[3]), b2 = (css[0] + css[1]) + (css[2] + css[3]);
+                    if (fe == fA) { s0 += a; ss0 += b2; } else { s1v += a; ss1v += b2; }
+                }
+                if ((c & 1) && !(p.dbg_skip_epilogue & 64)) {  // a 64-pixel half-box is complete
+                    fence_proxy_async();                   // generic-proxy writes -> visible to the TMA store
+                    if (leader_t) bulk_wait_read<0>();     // the previous half-box store (other 64 rows) has left shared memory
+                    named_bar_sync(1 + box, 64);           // both channel quarters wrote this half-box; the other one is free again
+                    if (leader_t) {
+                        tma_store_2d(&tmO, stg + (c >> 1) * 8192, (quarter >> 1) * 64, (int)(qh + 64 * (c >> 1)));  // rows >= Q are clipped
+                        bulk_commit();
+                    }
+                }
+            }
+            if (p.stat_part) {
+                s0 = warp_sum(s0); ss0 = warp_sum(ss0); s1v = warp_sum(s1v); ss1v = warp_sum(ss1v);
+                if (lane == 0) {
+                    float2* sp = reinterpret_cast<float2*>(p.stat_part) + ((size_t)tile * 8 + ew) * 2;
+                    sp[0] = make_float2(s0, ss0);
+                    sp[1] = make_float2(s1v, ss1v);
+                }
+            }
+        }
+        if (leader_t) bulk_wait_all<0>();
     } else {
         // ================= epilogue (warps 3..10) =================
         // The accumulator is transposed (TMEM lane = output channel, column = pixel).  Measured (tools/conv_bench.py history):
@@ -573,13 +816,16 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     // Round-2 A/B on B200 (tools/conv_bench.py, 128->128 @64x64, 2048 frames, residual): two-phase 2.144 ms (1154 TFLOP/s), fragment
     // 2.207 ms (1121): the fragment path moves the same bytes through shared memory (the residual now arrives there too) and pays ~3x
     // the instructions for the per-value border-class fold, so it stays an experiment.
-    p.epi_mode = (g_cz_swap == 4 && p.FS >= kCtPix && ((uintptr_t)a->out & 127) == 0 && (!a->residual || ((uintptr_t)a->residual & 127) == 0)) ? 1 : 0;
+    const int swap_mode = g_cz_swap & 0xff, bst_cap = (g_cz_swap >> 8) & 0xff, dbg_bits = (g_cz_swap >> 16) & 0xff;  // bits 8+: debug cap on the weight pipeline depth
+    const bool tma_epi_ok = p.FS >= kCtPix && (swap_mode != 5 || (W >= 33 && H >= 8)) && ((uintptr_t)a->out & 127) == 0 && (!a->residual || ((uintptr_t)a->residual & 127) == 0);
+    p.epi_mode = (swap_mode == 4 && tma_epi_ok) ? 1 : ((swap_mode == 5 && tma_epi_ok) ? 2 : 0);
     const size_t bars_bytes = (4 + 2 * kCzMaxBStages + 4 + 4) * 8 + 16;
     const size_t tail = p.epi_mode == 1 ? 65536 + bars_bytes + 2 * 2 * 128 * 16 + 64
-                                        : bars_bytes + 2 * 64 * kCtPitch * 4 + 2 * 64 * 16 + 64;
+                        : (p.epi_mode == 2 ? 65536 + bars_bytes + 64 : bars_bytes + 2 * 64 * kCtPitch * 4 + 2 * 64 * 16 + 64);
     const long long budget = 225 * 1024 - 1024 - 2 * (long long)p.a_stage_bytes - (long long)tail;
     int bst = (int)(budget / w_stage_bytes);
     if (bst > kCzMaxBStages) bst = kCzMaxBStages;
+    if (bst_cap > 0 && bst > bst_cap) bst = bst_cap;
     VPT_CHECK(bst >= 2, "vpt_conv3x3_zp: not enough shared memory for the weight pipeline (W=%d)", W);
     p.b_stages = bst;
     p.stage_off = 2 * p.a_stage_bytes + bst * (int)w_stage_bytes;
@@ -587,13 +833,13 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     CUtensorMap tmX, tmW, tmO, tmR;
     memset(&tmO, 0, sizeof(tmO));
     memset(&tmR, 0, sizeof(tmR));
-    if (p.epi_mode == 1) {  // output / residual [Q][128] bf16: boxes of 128 pixel rows x 64 channels (128-byte rows, SWIZZLE_128B)
+    if (p.epi_mode != 0) {  // output / residual [Q][128] bf16: boxes of 128 pixel rows x 64 channels (128-byte rows, SWIZZLE_128B)
         cuuint64_t dims[2] = {128, (cuuint64_t)p.Q};
         cuuint64_t strides[1] = {256};
-        cuuint32_t box[2] = {64, 128};
+        cuuint32_t box[2] = {64, (cuuint32_t)(p.epi_mode == 2 ? 64 : 128)};  // v3 stores half-boxes
         int r = make_tmap_bf16(&tmO, a->out, 2, dims, strides, box);
         if (r) return r;
-        if (a->residual) {
+        if (a->residual && p.epi_mode == 1) {
             r = make_tmap_bf16(&tmR, a->residual, 2, dims, strides, box);
             if (r) return r;
         }
@@ -620,7 +866,7 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     VPT_CHECK(!a->Ef || a->mr, "vpt_conv3x3_zp: Ef needs mr = (0, rstd) per frame");
     VPT_CHECK(!a->res_scale == !a->res_shift && (!a->res_scale || a->residual), "vpt_conv3x3_zp: res_scale / res_shift come as a pair, with a residual");
     VPT_CHECK(!(p.epi_mode == 1 && (a->Ef || a->res_scale)), "vpt_conv3x3_zp: the fragment-epilogue experiment (swap mode 4) does not implement Ef / res_scale");
-    p.dbg_skip_epilogue = (g_cz_swap == 2) ? 2 : 0;  // 2: no epilogue work (MMA-rate experiment)
+    p.dbg_skip_epilogue = (swap_mode == 2) ? 2 : (dbg_bits & 0xf0);  // v3 experiment bits: 16 no STS, 32 no classification, 64 no TMA store, 128 no LDTM  // 2: no epilogue work (MMA-rate experiment)
     static bool attr_set = false;
     if (!attr_set) {
         VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -682,7 +928,8 @@ extern "C" int vpt_set_conv_swap_mode(int32_t on) {
 /* Statistics plumbing of the fragment-epilogue kernel (Cout == 128): number of floats of its partial buffer ([tiles][8 warps][2 frame
  * slots] float2), 0 when another kernel / epilogue handles this shape (then vpt_conv_zp_stat_parts + vpt_stats_finalize apply). */
 extern "C" int64_t vpt_conv_zp_t_stat_floats(int32_t F, int32_t H, int32_t W, int32_t Cout) {
-    if (Cout != 128 || vpt::g_cz_swap != 4 || (H + 1) * (W + 1) < vpt::kCtPix) return 0;
+    const int mode = vpt::g_cz_swap & 0xff;
+    if (Cout != 128 || (mode != 4 && mode != 5) || (H + 1) * (W + 1) < vpt::kCtPix || (mode == 5 && (W < 33 || H < 8))) return 0;
     const long long Q = (long long)F * (H + 1) * (W + 1);
     return ((Q + vpt::kCtPix - 1) / vpt::kCtPix) * 8 * 2 * 2;
 }
