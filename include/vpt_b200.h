@@ -329,7 +329,10 @@ int vpt_relu_mask(const void* dout, const void* out, void* dz, int64_t n, void* 
  * pattern is the ReLU mask the backward needs)                                              lib/impala_cnn.py:50-52 */
 int vpt_add_stats(const void* a, const void* b, void* out, float* stat_part, int64_t groups, int64_t elems_per_group, void* stream);
 int vpt_add_stat_parts(int64_t elems_per_group);
-/* Weight gradient on the tcgen05 GEMM (csrc/gemm_tc.cuh with both operands MN-major, K split over CTAs + fixed-order reduction):
+/* Weight-gradient kernel choice: 1 (default) = tap-pairing kernel (csrc/wgrad_tc.cuh: taps whose shifts differ by one row share one
+ * activation span and one gradient tile in shared memory, two TMEM accumulators), 0 = one GEMM tile per tap (csrc/gemm_tc.cuh).  A-B knob. */
+int vpt_set_wgrad_mode(int32_t mode);
+/* Weight gradient on the tcgen05 GEMM (both operands MN-major, K split over CTAs + fixed-order reduction):
  *   out fp32 [M][ntaps*N],  out[m][tap*N + n] = sum_{k in [0,R)} a[k][m] * b[k + shifts[tap]][n]   (rows outside [0,R) are 0)
  * a bf16 [R][lda] = output gradient (M columns), b bf16 [R][ldb] = (normalised) layer input (N columns); no transposes needed.
  * Linear: ntaps = 1, shift 0.  3x3 conv on ZP tensors: ntaps = 9, shifts[tap] = (ky-1)*(W+1) + (kx-1), out is [Cout][tap][Cin].

@@ -45,6 +45,9 @@ def test_relu_mask_and_residual_add():
     (256, 1024, 2048, [0]),                                                             # linear
     (8768, 256, 300, [0]),                                                              # heads (many M tiles, K tail)
     (792, 256, 96, [0]),                                 # q|k|v|r concat (M not a multiple of 64)
+    (384, 384, 3 * 33 * 33, [(ky - 1) * 33 + (kx - 1) for ky in range(3) for kx in range(3)]),  # 3x stack-1 shape: 3 m tiles x 2 n tiles
+    (64, 128, 700, [0, 5, 6, 100]),                      # a tap pair in the middle of unpaired taps
+    (256, 320, 1000, [-1, 0, 1]),                        # N tiles 256 + 64, one pair + one single
 ])
 def test_wgrad_matches_emulation(M, N, R, shifts):
     g = torch.Generator().manual_seed(1)
@@ -59,6 +62,13 @@ def test_wgrad_matches_emulation(M, N, R, shifts):
     wide = torch.randn(R, M + 64, generator=g).to(BF16)
     out2 = ops.wgrad(wide.to(DEV)[:, 64:], b.to(DEV), shifts)
     assert rel(out2, E.wgrad(wide[:, 64:], b, shifts)) < 1e-5
+    try:  # the one-GEMM-tile-per-tap kernel of round 1 (A-B knob) gives the same sums
+        nat.lib().vpt_set_wgrad_mode(0)
+        out0 = ops.wgrad(a.to(DEV), b.to(DEV), shifts)
+        nat.device_check()
+    finally:
+        nat.lib().vpt_set_wgrad_mode(1)
+    assert rel(out0, ref) < 1e-5
 
 
 @pytest.mark.parametrize("rows,C,rpg,zp", [(2 * 81, 64, 81, (8, 8, 64)), (40, 256, 1, None), (6, 5 * 5 * 64, 1, (4, 4, 64)),

@@ -1,5 +1,5 @@
 #!/bin/bash
 # One gpurun call = one batch of GPU work (this is the script the builder edits between calls; it travels with the repo snapshot).
 mkdir -p gpurun_out
-echo "=== conv tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "conv3x3_zp or two_norm" 2>&1 | tail -15
-echo "=== conv bench"; timeout 600 python tools/conv_bench.py 2>&1 | tail -20
+echo "=== training tests"; timeout 1500 python -m pytest tests/test_gpu_training.py -x -q -m gpu 2>&1 | tail -5
+echo "=== bc bench"; timeout 900 python tools/bc_bench.py --ops 2>&1 | tail -30

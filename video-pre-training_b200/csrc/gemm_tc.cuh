@@ -691,10 +691,20 @@ __global__ void __launch_bounds__(256) sum_splits_kernel(const float4* __restric
 
 }  // namespace vpt
 
+namespace vpt {  // tap-pairing kernel (wgrad_tc.cuh)
+int wgrad_mode();
+long long wgrad_pair_max_splits(int M, int N, int ntaps, long long R);
+int launch_wgrad_pair(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t M, int32_t N, int64_t R, const int32_t* shifts, int32_t ntaps,
+                      float* out, void* workspace, int64_t workspace_bytes, void* stream);
+}  // namespace vpt
+
 extern "C" int64_t vpt_wgrad_workspace_bytes(int32_t M, int32_t N, int32_t ntaps, int64_t R) {
-    if (M <= 0 || N <= 0 || ntaps <= 0 || R <= 0) return 0;
+    if (M <= 0 || N <= 0 || ntaps <= 0 || ntaps > 9 || R <= 0) return 0;
     const vpt::WgradPlan w = vpt::wgrad_plan(M, N, ntaps, R);
-    return w.splits > 1 ? (int64_t)w.splits * M * N * ntaps * 4 : 0;
+    long long splits = w.splits;
+    const long long sp = vpt::wgrad_pair_max_splits(M, N, ntaps, R);  // either kernel may run (vpt_set_wgrad_mode)
+    if (sp > splits) splits = sp;
+    return splits > 1 ? (int64_t)splits * M * N * ntaps * 4 : 0;
 }
 
 extern "C" int vpt_wgrad_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int32_t M, int32_t N, int64_t R, const int32_t* shifts,
@@ -706,6 +716,7 @@ extern "C" int vpt_wgrad_bf16(const void* a, int64_t lda, const void* b, int64_t
               "vpt_wgrad_bf16: M, N and the row strides must be multiples of 8 (M=%d N=%d lda=%lld ldb=%lld)", M, N, (long long)lda, (long long)ldb);
     VPT_CHECK(R < 2147483647LL - 4096, "vpt_wgrad_bf16: too many rows for 32-bit TMA coordinates");
     VPT_CHECK(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0 && ((uintptr_t)out & 15) == 0, "vpt_wgrad_bf16: pointers must be 16-byte aligned");
+    if (wgrad_mode() == 1) return launch_wgrad_pair(a, lda, b, ldb, M, N, R, shifts, ntaps, out, workspace, workspace_bytes, stream);
     const WgradPlan w = wgrad_plan(M, N, ntaps, R);
     const long long out_elems = (long long)M * N * ntaps;
     VPT_CHECK(w.splits == 1 || (workspace && workspace_bytes >= (int64_t)w.splits * out_elems * 4),

@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace vpt
 
 #include "gemm_tc.cuh"
+#include "wgrad_tc.cuh"
 #include "gemv_small.cuh"
 #include "conv_zp.cuh"
 #include "conv_zp_t.cuh"
