@@ -30,7 +30,7 @@ extern "C" {
 #define VPT_ERR_CUDA (-2)   /* a CUDA runtime / driver call failed */
 #define VPT_ERR_DEVICE (-3) /* a kernel recorded a device-side protocol error (watchdog) */
 
-#define VPT_ABI_VERSION 2
+#define VPT_ABI_VERSION 3
 
 const char* vpt_last_error(void);
 int vpt_abi_version(void);
@@ -139,7 +139,7 @@ int vpt_set_conv_pair_mode(int32_t on);
 /* 1 (default): Cout == 128 layers run the operand-swapped kernel (channels as UMMA M, 256 pixels as N; see
  * csrc/conv_zp_t.cuh); 0: the regular orientation.  Changes vpt_conv_zp_stat_parts(128).  Tuning / A-B knob. */
 int vpt_set_conv_swap_mode(int32_t on);
-int vpt_conv_zp_stat_parts(int32_t Cout);
+int vpt_conv_zp_stat_parts(int32_t F, int32_t H, int32_t W, int32_t Cout);  /* (few frames use narrower weight tiles, hence more partials per row) */
 /* Cout == 128 with the operand-swapped kernel's experimental fragment epilogue (vpt_set_conv_swap_mode(4)): its statistics partials are per (tile, warp, frame slot),
  * not per row.  vpt_conv_zp_t_stat_floats > 0 <=> pass a float buffer of that many elements as stat_part and finalise it with
  * vpt_conv_zp_t_stats_finalize (mr[f] = mean, rstd over the H*W*128 interior values of frame f). */
@@ -216,8 +216,8 @@ int vpt_conv3d_stat_parts(int32_t H, int32_t W, int32_t C);
  *   stat_part float2 [F][vpt_pool_stat_parts()] */
 int vpt_maxpool3s2(const void* in, void* out, float* stat_part, float* chan_part, int32_t F, int32_t H, int32_t W, int32_t C, int32_t zp,
                    void* stream);  /* chan_part: NULL or float2 [F][P][C] per-channel partials (needs C/8 | 256); with chan_part BOTH partial
-                                      buffers hold P = vpt_pool_chan_parts(H, W, C) entries per frame instead of vpt_pool_stat_parts */
-int vpt_pool_chan_parts(int32_t H, int32_t W, int32_t C);
+                                      buffers hold P = vpt_pool_chan_parts(F, H, W, C) entries per frame instead of vpt_pool_stat_parts */
+int vpt_pool_chan_parts(int32_t F, int32_t H, int32_t W, int32_t C);
 /* Two-norm composition: the post-pool GroupNorm `n` (lib/impala_cnn.py:119) is not run as a pass; its effect is folded into the two
  * consumers of x0 = n(y1): block 0's conv0 (input y1, weights W*gamma0*gamma_n, per-frame table Ef) and conv1 (residual y1 with a
  * per-frame affine).  From the per-channel (sum, sumsq) partials of y1 [F][NP][C] (vpt_firstconv_pool / vpt_maxpool3s2), gamma_n / beta_n
@@ -229,7 +229,7 @@ int vpt_pool_chan_parts(int32_t H, int32_t W, int32_t C);
 int vpt_norm2_fold(const float* chan_part, int32_t NP, int32_t C, int64_t npix, const float* gamma_n, const float* beta_n, const float* Ta,
                    const float* Tb, const float* Tc, const float* Td, int32_t Cout, float eps, float* mrE, float* Ef, float* res_scale,
                    float* res_shift, int64_t F, void* stream);
-int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C);
+int vpt_pool_stat_parts(int32_t F, int32_t H, int32_t W, int32_t C);
 
 /* out[m][c] = (in[m][c] - mean_g) * rstd_g * gamma[c] + beta[c],  g = m / rows_per_group   (bf16 in, bf16 out)
  * = nn.GroupNorm(1, C) on NHWC rows (lib/impala_cnn.py:119) and nn.LayerNorm(C) (lib/util.py:195, lib/policy.py:214).

@@ -21,7 +21,7 @@ def test_header_symbols_are_bound_and_exported():
     l = ctypes.CDLL(nat.LIB_PATH)
     for n in names:
         assert hasattr(l, n), f"{n} declared in include/vpt_b200.h but not exported"
-    assert l.vpt_abi_version() == 2
+    assert l.vpt_abi_version() == 3
 
 
 def test_library_is_sm100a_tcgen05_tma():

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libvpt_b200.so")
 SRC = os.path.join(_HERE, "csrc", "vpt_b200.cu")
 HEADER = os.path.join(_ROOT, "include", "vpt_b200.h")
 
-ABI_VERSION = 2  # == VPT_ABI_VERSION in include/vpt_b200.h (checked against the loaded library)
+ABI_VERSION = 3  # == VPT_ABI_VERSION in include/vpt_b200.h (checked against the loaded library)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
@@ -81,7 +81,7 @@ SIGNATURES = {
     "vpt_gemm_stat_parts": (_I, [_I]),
     "vpt_set_default_cluster": (_I, [_I]),
     "vpt_conv3x3_zp": (_I, [C.POINTER(ConvZpArgs), _P]),
-    "vpt_conv_zp_stat_parts": (_I, [_I]),
+    "vpt_conv_zp_stat_parts": (_I, [_I, _I, _I, _I]),
     "vpt_conv_zp_t_stat_floats": (_L, [_I, _I, _I, _I]),
     "vpt_conv_zp_t_stats_finalize": (_I, [_P, _P, _I, _I, _I, _F, _P]),
     "vpt_set_conv_pair_mode": (_I, [_I]),
@@ -102,8 +102,8 @@ SIGNATURES = {
     "vpt_conv3d_stat_parts": (_I, [_I, _I, _I]),
     "vpt_maxpool3s2": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vpt_norm2_fold": (_I, [_P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _L, _P]),
-    "vpt_pool_stat_parts": (_I, [_I, _I, _I]),
-    "vpt_pool_chan_parts": (_I, [_I, _I, _I]),
+    "vpt_pool_stat_parts": (_I, [_I, _I, _I, _I]),
+    "vpt_pool_chan_parts": (_I, [_I, _I, _I, _I]),
     "vpt_affine_norm": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "vpt_affine_norm_zp": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vpt_norm_stat_parts": (_I, [_I, _I]),

@@ -546,6 +546,20 @@ extern int g_cz_swap_enabled();
 int launch_conv_zp_t_fwd(const vpt_conv_zp_args* a, void* stream);
 }  // namespace vpt
 
+namespace vpt {
+// Weight-tile width.  A handful of frames (rollout: F = 1, 1089 rows at 32 x 32): the launch is a read of the 1.2 MB weight tensor through
+// the few SMs that have a tile, so narrower weight tiles put more SMs (each fetching a slice) on it -- ~64 CTAs instead of 5.
+static inline void conv_zp_block_n(long long Q, int N, int* bn, int* nt) {
+    choose_block_n(N, bn, nt);
+    const long long tiles = (Q + 255) / 256;
+    if (tiles * *nt >= 32) return;
+    const int want = (int)((64 + tiles - 1) / tiles);
+    int t = *nt;
+    while (t < want && N % (2 * t) == 0 && N / (2 * t) >= 32 && (N / (2 * t)) % 16 == 0) t *= 2;
+    if (N % t == 0) { *nt = t; *bn = N / t; }
+}
+}  // namespace vpt
+
 extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     using namespace vpt;
     VPT_CHECK(a && a->x && a->w && a->out, "vpt_conv3x3_zp: null operand");
@@ -561,7 +575,7 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     p.Q = (long long)a->F * p.FS;
     VPT_CHECK(p.Q < 2147483647LL, "vpt_conv3x3_zp: too many rows for 32-bit TMA coordinates");
     p.N = N; p.cin = C; p.cin_blocks = C / 64;
-    choose_block_n(N, &p.block_n, &p.num_n_tiles);
+    conv_zp_block_n(p.Q, N, &p.block_n, &p.num_n_tiles);
     // measured (tools/conv_bench.py): SM pairs win for 256-wide weight tiles (+11-13 %), a single CTA with two 128-row
     // sub-tiles wins for <= 128 output channels; g_cz_pair: 0 = never, 1 = auto, 2 = always
     const bool pair = (g_cz_pair == 2 || (g_cz_pair == 1 && p.block_n > 128)) && (p.block_n % 16 == 0) && (p.Q > 256);
@@ -678,9 +692,9 @@ extern "C" int vpt_set_conv_pair_mode(int32_t on) {
     return VPT_OK;
 }
 
-extern "C" int vpt_conv_zp_stat_parts(int32_t Cout) {
+extern "C" int vpt_conv_zp_stat_parts(int32_t F, int32_t H, int32_t W, int32_t Cout) {
     if (Cout == 128 && vpt::g_cz_swap_enabled()) return 1;  // swapped kernel, round-1 epilogue: complete row sums (see vpt_conv_zp_t_stat_floats)
     int bn, nt;
-    vpt::choose_block_n(Cout, &bn, &nt);
+    vpt::conv_zp_block_n((long long)F * (H + 1) * (W + 1), Cout, &bn, &nt);
     return nt * 2;
 }

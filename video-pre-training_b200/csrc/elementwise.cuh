@@ -486,15 +486,24 @@ static inline int vpt_blocks_for(long long items, int per_block, int cap) {
     return (int)b;
 }
 
-extern "C" int vpt_pool_stat_parts(int32_t H, int32_t W, int32_t C) {
-    return vpt_blocks_for((long long)(H / 2) * (W / 2) * (C / 8), 2048, 64);
+// blocks per frame of the pooling kernel = entries per frame of its partial buffers.  A handful of frames (rollout: F = 1): enough blocks
+// to put work on every SM (a 64 x 64 x 256 frame would otherwise be pooled by 4 blocks: 64 us of a 1.3 ms step).  Only for F <= 16: the
+// partial count fixes the summation order of the statistics, and batch runs promise bit-identical rows whatever the batch size.
+static inline int pool_parts(int F, int H, int W, int C, int per_block, int cap) {
+    const long long items = (long long)(H / 2) * (W / 2) * (C / 8);
+    int p = vpt_blocks_for(items, per_block, cap);
+    if (F <= 16 && (long long)F * p < 2 * 148) {
+        long long want = (2 * 148 + F - 1) / F, most = items / 256 > 0 ? items / 256 : 1;  // at least one item per thread
+        if (want > most) want = most;
+        if (want > 256) want = 256;
+        if (want > p) p = (int)want;
+    }
+    return p;
 }
+extern "C" int vpt_pool_stat_parts(int32_t F, int32_t H, int32_t W, int32_t C) { return pool_parts(F, H, W, C, 2048, 64); }
 /* With per-channel partials every block ends with a 16 KB shared-memory reduction: 4x fewer, 4x longer blocks amortise it
  * (measured: the pool was 50 % slower with the per-frame block count above). */
-extern "C" int vpt_pool_chan_parts(int32_t H, int32_t W, int32_t C) {
-    const int p = vpt_pool_stat_parts(H, W, C) / 4;
-    return p < 1 ? 1 : p;
-}
+extern "C" int vpt_pool_chan_parts(int32_t F, int32_t H, int32_t W, int32_t C) { return pool_parts(F, H, W, C, 8192, 16); }
 
 extern "C" int vpt_norm2_fold(const float* chan_part, int32_t NP, int32_t C, int64_t npix, const float* gamma_n, const float* beta_n, const float* Ta,
                               const float* Tb, const float* Tc, const float* Td, int32_t Cout, float eps, float* mrE, float* Ef, float* res_scale,
@@ -515,7 +524,7 @@ extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, float
     VPT_CHECK(!chan_part || (C >= 8 && 256 % (C / 8) == 0), "vpt_maxpool3s2: per-channel partials need C/8 to divide 256 (C=%d)", C);
     VPT_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vpt_maxpool3s2: need even H, W and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
     VPT_CHECK(F <= 65535, "vpt_maxpool3s2: at most 65535 frames per call (got %d)", F);
-    dim3 grid(chan_part ? vpt_pool_chan_parts(H, W, C) : vpt_pool_stat_parts(H, W, C), F);
+    dim3 grid(chan_part ? vpt_pool_chan_parts(F, H, W, C) : vpt_pool_stat_parts(F, H, W, C), F);
     if (chan_part)
         maxpool3s2_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
                                                                       reinterpret_cast<float2*>(stat_part), reinterpret_cast<float2*>(chan_part), H, W, C / 8, zp ? 1 : 0);

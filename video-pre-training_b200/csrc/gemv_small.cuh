@@ -13,31 +13,75 @@ namespace vpt {
 constexpr int kGsMaxM = 8;
 constexpr int kGsThreads = 256;
 
+constexpr int kGsUnroll = 8;  // 16-byte weight loads in flight per lane (8 x 512 B per warp: what it takes to cover HBM latency with few warps)
+
+__device__ __forceinline__ uint4 ld_stream16(const uint4* p) {  // read-once weights: do not displace the activations in L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// kWpc warps share one output column (each streams a contiguous 1/kWpc of the K range; partial sums meet in shared memory): used when
+// N is small, so that the layer still has thousands of 16-byte loads in flight per SM (N = 256, K = 73984 `dense`: 32 CTAs otherwise).
+template <int kWpc>
 __global__ void __launch_bounds__(kGsThreads) gemv_small_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
                                                                   const GemmParams p) {
+    __shared__ float s_part[kGsThreads / 32][kGsMaxM];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = p.M, K8 = p.K >> 3;
-    for (int n = blockIdx.x * (kGsThreads / 32) + warp; n < p.N; n += gridDim.x * (kGsThreads / 32)) {
+    constexpr int kCols = (kGsThreads / 32) / kWpc;  // output columns per CTA
+    const int kpart = warp % kWpc;
+    const int chunk = ((K8 + kWpc - 1) / kWpc + 31) / 32 * 32;
+    const int k_begin = kpart * chunk, k_end = min(K8, k_begin + chunk);
+    for (int n0 = blockIdx.x * kCols; n0 < p.N; n0 += gridDim.x * kCols) {
+        const int n = n0 + warp / kWpc;
         float acc[kGsMaxM];
 #pragma unroll
         for (int m = 0; m < kGsMaxM; ++m) acc[m] = 0.f;
-        const uint4* wrow = reinterpret_cast<const uint4*>(W + (size_t)n * p.K);
-        for (int k = lane; k < K8; k += 32) {
-            const uint4 w = __ldg(wrow + k);
-            const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+        if (n < p.N) {
+            const uint4* wrow = reinterpret_cast<const uint4*>(W + (size_t)n * p.K);
+            for (int k0 = k_begin + lane; k0 < k_end; k0 += 32 * kGsUnroll) {
+                uint4 w[kGsUnroll];
 #pragma unroll
-            for (int m = 0; m < kGsMaxM; ++m) {
-                if (m < M) {
-                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(A + (size_t)m * p.K) + k);
-                    acc[m] = fmaf(bf16_lo(a.x), wf[0], acc[m]); acc[m] = fmaf(bf16_hi(a.x), wf[1], acc[m]);
-                    acc[m] = fmaf(bf16_lo(a.y), wf[2], acc[m]); acc[m] = fmaf(bf16_hi(a.y), wf[3], acc[m]);
-                    acc[m] = fmaf(bf16_lo(a.z), wf[4], acc[m]); acc[m] = fmaf(bf16_hi(a.z), wf[5], acc[m]);
-                    acc[m] = fmaf(bf16_lo(a.w), wf[6], acc[m]); acc[m] = fmaf(bf16_hi(a.w), wf[7], acc[m]);
+                for (int u = 0; u < kGsUnroll; ++u) w[u] = (k0 + 32 * u < k_end) ? ld_stream16(wrow + k0 + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int u = 0; u < kGsUnroll; ++u) {
+                    const int k = k0 + 32 * u;
+                    if (k >= k_end) break;
+                    const float wf[8] = {bf16_lo(w[u].x), bf16_hi(w[u].x), bf16_lo(w[u].y), bf16_hi(w[u].y),
+                                         bf16_lo(w[u].z), bf16_hi(w[u].z), bf16_lo(w[u].w), bf16_hi(w[u].w)};
+#pragma unroll
+                    for (int m = 0; m < kGsMaxM; ++m) {
+                        if (m < M) {
+                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(A + (size_t)m * p.K) + k);
+                            acc[m] = fmaf(bf16_lo(a.x), wf[0], acc[m]); acc[m] = fmaf(bf16_hi(a.x), wf[1], acc[m]);
+                            acc[m] = fmaf(bf16_lo(a.y), wf[2], acc[m]); acc[m] = fmaf(bf16_hi(a.y), wf[3], acc[m]);
+                            acc[m] = fmaf(bf16_lo(a.z), wf[4], acc[m]); acc[m] = fmaf(bf16_hi(a.z), wf[5], acc[m]);
+                            acc[m] = fmaf(bf16_lo(a.w), wf[6], acc[m]); acc[m] = fmaf(bf16_hi(a.w), wf[7], acc[m]);
+                        }
+                    }
                 }
             }
         }
 #pragma unroll
         for (int m = 0; m < kGsMaxM; ++m) acc[m] = warp_sum(acc[m]);
+        if (kWpc > 1) {  // fixed-order sum of the K parts (block-uniform control flow: every warp reaches the barriers)
+            if (lane == 0) {
+#pragma unroll
+                for (int m = 0; m < kGsMaxM; ++m) s_part[warp][m] = acc[m];
+            }
+            __syncthreads();
+            if (kpart == 0) {
+#pragma unroll
+                for (int m = 0; m < kGsMaxM; ++m) {
+                    float t = 0.f;
+                    for (int q = 0; q < kWpc; ++q) t += s_part[warp + q][m];
+                    acc[m] = t;
+                }
+            }
+            __syncthreads();
+        }
+        if (n >= p.N || kpart != 0) continue;
         if (lane == 0) {
             const float s1 = p.S1 ? __ldg(p.S1 + n) : 0.f, s2 = p.S2 ? __ldg(p.S2 + n) : 0.f;
 #pragma unroll
@@ -118,10 +162,16 @@ static int try_launch_gemv_small(const vpt_gemm_args* a, void* stream) {
     int bn, nt;
     choose_block_n(a->N, &bn, &nt);
     const int P = nt * 2;  // == vpt_gemm_stat_parts(N)
-    int grid = (a->N + kGsThreads / 32 - 1) / (kGsThreads / 32);
+    // one warp per column when that already gives >= ~4 CTAs per SM, else the 8 warps of a CTA share a column (K split)
+    const bool split = a->N < 4 * num_sms() * (kGsThreads / 32) / 8 && a->K >= 2048;
+    int grid = split ? a->N : (a->N + kGsThreads / 32 - 1) / (kGsThreads / 32);
     if (grid > 8 * 148) grid = 8 * 148;
-    gemv_small_kernel<<<grid, kGsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->A),
-                                                                     reinterpret_cast<const __nv_bfloat16*>(a->B), p);
+    if (split)
+        gemv_small_kernel<kGsThreads / 32><<<grid, kGsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->A),
+                                                                                          reinterpret_cast<const __nv_bfloat16*>(a->B), p);
+    else
+        gemv_small_kernel<1><<<grid, kGsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->A),
+                                                                            reinterpret_cast<const __nv_bfloat16*>(a->B), p);
     VPT_LAUNCH_CHECK();
     if (a->stat_part) {
         row_stats_small_kernel<<<a->M, 256, 0, (cudaStream_t)stream>>>(p, P);

@@ -97,7 +97,7 @@ def conv3x3_zp(x, Wb, H, W, *, mr=None, S1=None, S2=None, relu=1, residual=None,
     if out is None:
         out = torch.empty((F_, H + 1, W + 1, Cout), dtype=BF16, device=x.device)
     assert out.is_contiguous() and tuple(out.shape) == (F_, H + 1, W + 1, Cout)
-    P = nat.lib().vpt_conv_zp_stat_parts(Cout)
+    P = nat.lib().vpt_conv_zp_stat_parts(F_, H, W, Cout)
     tfl = nat.lib().vpt_conv_zp_t_stat_floats(F_, H, W, Cout)  # > 0: the swapped kernel's fragment epilogue (per-tile partials)
     part = None
     if want_stats:
@@ -218,7 +218,7 @@ def maxpool3s2(x, zp=True, want_chan=False):
     F_, H, W, Cc = x.shape[0], x.shape[1] - z, x.shape[2] - z, x.shape[3]
     out = torch.empty((F_, H // 2 + z, W // 2 + z, Cc), dtype=BF16, device=x.device)
     with_chan = want_chan and Cc >= 8 and 256 % (Cc // 8) == 0
-    P = nat.lib().vpt_pool_chan_parts(H, W, Cc) if with_chan else nat.lib().vpt_pool_stat_parts(H, W, Cc)
+    P = nat.lib().vpt_pool_chan_parts(F_, H, W, Cc) if with_chan else nat.lib().vpt_pool_stat_parts(F_, H, W, Cc)
     part = torch.empty((F_, P, 2), dtype=F32, device=x.device)
     chan = torch.empty((F_, P, Cc, 2), dtype=F32, device=x.device) if with_chan else None
     nat.check(nat.lib().vpt_maxpool3s2(_p(x), _p(out), _p(part), _p(chan), F_, H, W, Cc, z, _stream()), "vpt_maxpool3s2")
