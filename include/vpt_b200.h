@@ -332,6 +332,10 @@ int vpt_add_stat_parts(int64_t elems_per_group);
 /* Weight-gradient kernel choice: 1 (default) = tap-pairing kernel (csrc/wgrad_tc.cuh: taps whose shifts differ by one row share one
  * activation span and one gradient tile in shared memory, two TMEM accumulators), 0 = one GEMM tile per tap (csrc/gemm_tc.cuh).  A-B knob. */
 int vpt_set_wgrad_mode(int32_t mode);
+/* 1: forward-path kernels are launched with the programmatic-stream-serialization attribute (programmatic dependent launch): the next
+ * kernel is scheduled while the previous one drains and blocks in griddepcontrol.wait until that one has completed and flushed, so only
+ * launch latency overlaps.  Default 0 (measured neutral on the rollout CUDA graph; results are bit-identical either way). */
+int vpt_set_pdl(int32_t on);
 /* Weight gradient on the tcgen05 GEMM (both operands MN-major, K split over CTAs + fixed-order reduction):
  *   out fp32 [M][ntaps*N],  out[m][tap*N + n] = sum_{k in [0,R)} a[k][m] * b[k + shifts[tap]][n]   (rows outside [0,R) are 0)
  * a bf16 [R][lda] = output gradient (M columns), b bf16 [R][ldb] = (normalised) layer input (N columns); no transposes needed.

@@ -197,6 +197,30 @@ def test_graphed_act_matches_eager_and_logit_mask():
     nat.device_check()
 
 
+def test_programmatic_dependent_launch_is_invisible():
+    """vpt_set_pdl(1): every forward kernel starts with griddepcontrol.launch_dependents + griddepcontrol.wait, so letting the next launch be
+    scheduled early must not change a single bit -- eager streams of launches at full 2x size (big grids) and at the rollout size."""
+    kw = vpt_b200.policy_kwargs("2x")
+    pol, sd, cfg = make_policy(kw, pert=True, seed=4)
+    pol = pol.to(DEV)
+    g = torch.Generator().manual_seed(23)
+    for B, T in ((3, 40), (1, 1)):
+        img = torch.randint(0, 256, (B, T, 128, 128, 3), dtype=torch.uint8, generator=g).to(DEV)
+        first = torch.zeros(B, T, dtype=torch.bool, device=DEV)
+        outs = []
+        for on in (0, 1, 1):
+            nat.lib().vpt_set_pdl(on)
+            try:
+                (pd, v, _), st = pol({"img": img}, first, pol.initial_state(B))
+                torch.cuda.synchronize()
+            finally:
+                nat.lib().vpt_set_pdl(0)
+            outs.append((pd["buttons"].clone(), pd["camera"].clone(), v.clone(), st[-1][1][0].clone()))
+        nat.device_check()
+        for o in outs[1:]:
+            assert all(torch.equal(a, b) for a, b in zip(outs[0], o)), (B, T)
+
+
 def test_graphed_act_follows_weight_changes():
     """a captured rollout graph holds raw pointers to the kernel-layout weights; after load_state_dict / an
     optimizer step it must re-layout and re-capture instead of replaying stale (or freed) weights."""

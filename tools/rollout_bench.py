@@ -27,8 +27,8 @@ for _ in range(a.steps):
     _ = ac["buttons"].cpu()  # the env needs the action on the host every step (agent.py:151-164)
 t1 = time.perf_counter()
 print(f"eager : {a.width} B={B} T=1: {(t1-t0)/a.steps*1e3:.3f} ms/step  ({B*a.steps/(t1-t0):.0f} frames/s)")
-if hasattr(pol, "make_graphed_act"):
-    step = pol.make_graphed_act(B)
+for pdl in (False, True):
+    step = pol.make_graphed_act(B, pdl=pdl)
     st = pol.initial_state(B)
     for _ in range(5):
         ac, st, res = step({"img": img}, first, st)
@@ -38,7 +38,13 @@ if hasattr(pol, "make_graphed_act"):
         ac, st, res = step({"img": img}, first, st)
         _ = ac["buttons"].cpu()
     t1 = time.perf_counter()
-    print(f"graph : {a.width} B={B} T=1: {(t1-t0)/a.steps*1e3:.3f} ms/step  ({B*a.steps/(t1-t0):.0f} frames/s)")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        ac, st, res = step({"img": img}, first, st)
+    e1.record(); torch.cuda.synchronize()
+    print(f"graph pdl={int(pdl)}: device {e0.elapsed_time(e1)/a.steps:.3f} ms/step")
+    print(f"graph pdl={int(pdl)}: {a.width} B={B} T=1: {(t1-t0)/a.steps*1e3:.3f} ms/step  ({B*a.steps/(t1-t0):.0f} frames/s)")
     # parity: graphed step == eager step on the same inputs (deterministic action)
     st_a, st_b = pol.initial_state(B), pol.initial_state(B)
     for _ in range(3):

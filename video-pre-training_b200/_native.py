@@ -87,6 +87,7 @@ SIGNATURES = {
     "vpt_set_conv_pair_mode": (_I, [_I]),
     "vpt_set_conv_swap_mode": (_I, [_I]),
     "vpt_set_wgrad_mode": (_I, [_I]),
+    "vpt_set_pdl": (_I, [_I]),
     "vpt_debug_set": (_I, [_I, _I]),
     "vpt_firstconv_pool": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vpt_firstconv_stat_parts": (_I, [_I, _I, _I, _I]),

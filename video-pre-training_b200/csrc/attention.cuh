@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kAttThreads) attention_kernel(
     const float* __restrict__ R, long long ld_r, const float* __restrict__ b_nd, const uint8_t* __restrict__ first,
     long long first_stride, const uint8_t* __restrict__ smask, __nv_bfloat16* __restrict__ out, int t, int maxlen, int heads,
     int nbasis, int causal) {
+    pdl_sync();
     extern __shared__ __align__(16) uint8_t att_smem[];
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(att_smem);
     __nv_bfloat16* Ks = Qs + kAttBQ * kAttPitch;
@@ -242,7 +243,7 @@ extern "C" int vpt_attention(const void* Q, const void* Kf, const void* Vf, cons
         attr = smem;
     }
     dim3 grid((t + kAttBQ - 1) / kAttBQ, heads, B);
-    attention_kernel<<<grid, kAttThreads, smem, (cudaStream_t)stream>>>(
+    launch_k(attention_kernel, dim3(grid), dim3(kAttThreads), smem, (cudaStream_t)stream, 
         reinterpret_cast<const __nv_bfloat16*>(Q), reinterpret_cast<const __nv_bfloat16*>(Kf), reinterpret_cast<const __nv_bfloat16*>(Vf), R,
         ld_r, b_nd, first, first_stride, smask, reinterpret_cast<__nv_bfloat16*>(out), t, maxlen, heads, nb, causal);
     VPT_LAUNCH_CHECK();

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) codec_to_env_kernel(const long long* __re
                                                             const uint8_t* __restrict__ lut_btn, const uint8_t* __restrict__ lut_cam_off,
                                                             const double* __restrict__ cam_lut, int nbins, int njoint, long long n,
                                                             long long* __restrict__ out, int* __restrict__ bad) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long b = buttons[i], c = camera[i];
@@ -47,6 +48,7 @@ __device__ __forceinline__ int camera_bin(double v, const double* __restrict__ t
 __global__ void __launch_bounds__(256) codec_from_env_kernel(const long long* __restrict__ btn, const double* __restrict__ cam, const double* __restrict__ thr,
                                                               int nbins, const long long* __restrict__ strides, long long inventory_idx, long long n,
                                                               long long* __restrict__ out) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long* b = btn + i * kNumButtons;
@@ -84,7 +86,7 @@ extern "C" int vpt_codec_to_env(const int64_t* buttons, const int64_t* camera, c
                                 int32_t nbins, int32_t njoint, int64_t n, int64_t* out, int32_t* bad, void* stream) {
     using namespace vpt;
     VPT_CHECK(buttons && camera && lut_btn && lut_cam_off && cam_lut && out && bad && n > 0 && nbins > 0, "vpt_codec_to_env: bad argument");
-    codec_to_env_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(codec_to_env_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<const long long*>(buttons), reinterpret_cast<const long long*>(camera), lut_btn, lut_cam_off, cam_lut, nbins, njoint, n,
         reinterpret_cast<long long*>(out), bad);
     VPT_LAUNCH_CHECK();
@@ -95,7 +97,7 @@ extern "C" int vpt_codec_from_env(const int64_t* buttons, const double* camera, 
                                   int64_t inventory_idx, int64_t n, int64_t* out, void* stream) {
     using namespace vpt;
     VPT_CHECK(buttons && camera && thresholds && strides && out && n > 0 && nbins > 1, "vpt_codec_from_env: bad argument");
-    codec_from_env_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(codec_from_env_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<const long long*>(buttons), camera, thresholds, nbins, reinterpret_cast<const long long*>(strides), inventory_idx, n,
         reinterpret_cast<long long*>(out));
     VPT_LAUNCH_CHECK();

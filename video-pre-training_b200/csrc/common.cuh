@@ -30,6 +30,24 @@ void set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 #define VPT_LAUNCH_CHECK() VPT_CUDA(cudaGetLastError())
+static int g_pdl = 0;
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute when vpt_set_pdl(1)
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in the VPT_LAUNCH_CHECK() that follows
+}
+
 
 // device-side watchdog flag (defined by the including .cu): kernels that wait on mbarriers record a code here
 // instead of hanging forever.
@@ -40,6 +58,15 @@ __device__ unsigned int g_device_error = 0;
 // ------------------------------------------------------------------------------------------------------
 // small device utils
 // ------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel that may be launched with the attribute starts with pdl_sync(): it lets the NEXT
+// kernel of the stream be scheduled right away (its blocks then sit in their own pdl_sync()) and waits until the PREVIOUS kernel has
+// completed and flushed its memory -- so only launch latency and block scheduling overlap, never the data flow.  Without the attribute
+// both instructions are no-ops.  vpt_set_pdl(1) (default 0) makes the launchers below add the attribute (policy.GraphedAct(pdl=True);
+// measured neutral on the ~130-node rollout graph, tests/test_gpu_policy.py checks that it changes no bit).
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

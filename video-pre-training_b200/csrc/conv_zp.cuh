@@ -61,6 +61,7 @@ template <bool kPair>
 __global__ void __launch_bounds__(kCzThreads, 1)
 conv3x3_zp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                   const __grid_constant__ CUtensorMap tmR, const ConvZpParams p) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -649,7 +650,7 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
         long long grid = num_sms();
         if (grid <= 0) grid = 148;
         if (grid > tiles) grid = tiles;
-        conv3x3_zp_kernel<false><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmO, tmR, p);
+        launch_k(conv3x3_zp_kernel<false>, dim3((unsigned)grid), dim3(kCzThreads), smem_bytes, (cudaStream_t)stream, tmA, tmB, tmO, tmR, p);
         VPT_LAUNCH_CHECK();
         return VPT_OK;
     }
@@ -658,11 +659,13 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     cfg.blockDim = dim3(kCzThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (see pdl_sync() in common.cuh)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     static int max_pairs = 0;
@@ -679,6 +682,7 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     long long pairs = max_pairs;
     if (pairs > tiles) pairs = tiles;
     cfg.gridDim = dim3((unsigned)(pairs * 2));
+    cfg.numAttrs = g_pdl ? 2 : 1;
     VPT_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_zp_kernel<true>, tmA, tmB, tmO, tmR, p));
     return VPT_OK;
 }

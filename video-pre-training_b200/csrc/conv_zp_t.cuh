@@ -84,6 +84,7 @@ template <int kFold>
 __global__ void __launch_bounds__(kCzThreads, 1)
 conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmR, const ConvZpTParams p) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -878,9 +879,9 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     if (grid <= 0) grid = 148;
     if (grid > p.num_tiles) grid = p.num_tiles;
     VPT_CHECK(!(a->Ef && a->res_scale), "vpt_conv3x3_zp: Ef and res_scale are not combined (Cout == 128 kernel)");
-    if (a->Ef) conv3x3_zp_t_kernel<1><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
-    else if (a->res_scale) conv3x3_zp_t_kernel<2><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
-    else conv3x3_zp_t_kernel<0><<<(unsigned)grid, kCzThreads, smem_bytes, (cudaStream_t)stream>>>(tmX, tmW, tmO, tmR, p);
+    if (a->Ef) launch_k(conv3x3_zp_t_kernel<1>, dim3((unsigned)grid), dim3(kCzThreads), smem_bytes, (cudaStream_t)stream, tmX, tmW, tmO, tmR, p);
+    else if (a->res_scale) launch_k(conv3x3_zp_t_kernel<2>, dim3((unsigned)grid), dim3(kCzThreads), smem_bytes, (cudaStream_t)stream, tmX, tmW, tmO, tmR, p);
+    else launch_k(conv3x3_zp_t_kernel<0>, dim3((unsigned)grid), dim3(kCzThreads), smem_bytes, (cudaStream_t)stream, tmX, tmW, tmO, tmR, p);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
@@ -888,6 +889,7 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
 // epi_mode 1 statistics: mr[f] = (mean, rstd) of frame f from the per-(tile, warp, frame slot) partials; one warp per frame, fp64
 __global__ void __launch_bounds__(256) conv_zp_t_stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ mr, long long F, int FS,
                                                                         long long num_tiles, double inv_count, float eps) {
+    pdl_sync();
     const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (f >= F) return;
     const int lane = threadIdx.x & 31;
@@ -939,7 +941,7 @@ extern "C" int vpt_conv_zp_t_stats_finalize(const float* part, float* mr, int32_
     VPT_CHECK(part && mr && F > 0, "vpt_conv_zp_t_stats_finalize: null argument");
     const int FS = (H + 1) * (W + 1);
     const long long Q = (long long)F * FS, tiles = (Q + kCtPix - 1) / kCtPix;
-    conv_zp_t_stats_finalize_kernel<<<(unsigned)((F + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(conv_zp_t_stats_finalize_kernel, dim3((unsigned)((F + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<const float2*>(part), reinterpret_cast<float2*>(mr), F, FS, tiles, 1.0 / ((double)H * W * 128), eps);
     VPT_LAUNCH_CHECK();
     return VPT_OK;

@@ -33,6 +33,7 @@ __device__ __forceinline__ float2 block_sum2(float s, float ss) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ mr, long long G, int n_per_group,
                                       double inv_count, float eps) {
+    pdl_sync();
     // one warp per group; lanes stride over the partials, doubles for the final combination
     const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= G) return;
@@ -60,6 +61,7 @@ __global__ void stats_finalize_kernel(const float2* __restrict__ part, float2* _
 // large groups (a conv frame has thousands of per-row partials): one 256-thread block per group, fixed-order tree
 __global__ void __launch_bounds__(256) stats_finalize_block_kernel(const float2* __restrict__ part, float2* __restrict__ mr, int n_per_group,
                                                                      double inv_count, float eps) {
+    pdl_sync();
     __shared__ double red[2][8];
     const long long g = blockIdx.x;
     const float2* p = part + g * (long long)n_per_group;
@@ -108,6 +110,7 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 template <bool CHAN>
 __global__ void __launch_bounds__(256, CHAN ? 4 : 8) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                            float2* __restrict__ stat_part, float2* __restrict__ chan_part, int H, int W, int C8, int zp) {
+    pdl_sync();
     const int Ho = H >> 1, Wo = W >> 1;
     const int ipitch = W + zp, opitch = Wo + zp;  // ZP layout: one extra zero column (and row) per frame
     const long long f = blockIdx.y;
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(256) norm2_fold_kernel(const float2* __restric
                                                            const float* __restrict__ Tc, const float* __restrict__ Td, int Cout, float eps,
                                                            float2* __restrict__ mrE, float* __restrict__ Ef, float* __restrict__ res_scale,
                                                            float* __restrict__ res_shift) {
+    pdl_sync();
     const long long f = blockIdx.x;
     __shared__ double S[512], Q[512];
     __shared__ double red[256];
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(256) affine_norm_kernel(const uint4* __restric
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             uint4* __restrict__ out, float* __restrict__ out_f32,
                                                             float2* __restrict__ stat_part, long long items_per_group, int C8) {
+    pdl_sync();
     const long long g = blockIdx.y;
     const float2 st = __ldg(mr + g);
     const float mean = st.x, rstd = st.y;
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(256) affine_norm_kernel(const uint4* __restric
 __global__ void __launch_bounds__(256) affine_norm_zp_kernel(const uint4* __restrict__ in, const float2* __restrict__ mr,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                uint4* __restrict__ out, float2* __restrict__ stat_part, int H, int W, int C8) {
+    pdl_sync();
     const long long g = blockIdx.y;
     const float2 st = __ldg(mr + g);
     const float mean = st.x, rstd = st.y;
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(256) affine_norm_zp_kernel(const uint4* __rest
 __global__ void __launch_bounds__(256) affine_norm_zp_rows_kernel(const uint4* __restrict__ in, const float2* __restrict__ mr,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                     uint4* __restrict__ out, float2* __restrict__ stat_part, int H, int W, int C8) {
+    pdl_sync();
     const long long g = blockIdx.y;
     const float2 st = __ldg(mr + g);
     const float mean = st.x, rstd = st.y;
@@ -414,6 +421,7 @@ template <bool SRC_F32, bool DST_F32>
 __global__ void __launch_bounds__(256) copy_rows_kernel(const void* __restrict__ src0, const void* __restrict__ src1, long long src_bstride,
                                                           long long src_ld, long long src_off, void* __restrict__ dst0, void* __restrict__ dst1,
                                                           long long dst_bstride, long long dst_ld, long long dst_off, int rows, int cols8) {
+    pdl_sync();
     // blockIdx.z selects one of two (source, destination) pairs of identical geometry (K and V of a layer in one launch)
     const void* src = blockIdx.z ? src1 : src0;
     void* dst = blockIdx.z ? dst1 : dst0;
@@ -447,6 +455,7 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const void* __restrict__
 
 __global__ void state_mask_update_kernel(const uint8_t* __restrict__ mask_in, const uint8_t* __restrict__ first, long long first_stride,
                                          uint8_t* __restrict__ mask_out, int B, int t, int maxlen) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * maxlen) return;
     const int b = i / maxlen, j = i % maxlen;
@@ -466,14 +475,14 @@ extern "C" int vpt_stats_finalize(const float* stat_part, float* mr, int64_t G, 
     using namespace vpt;
     VPT_CHECK(stat_part && mr && G > 0 && n_per_group > 0 && count > 0, "vpt_stats_finalize: bad arguments");
     if (n_per_group >= 512) {
-        stats_finalize_block_kernel<<<(unsigned)G, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(stat_part),
+        launch_k(stats_finalize_block_kernel, dim3((unsigned)G), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float2*>(stat_part),
                                                                                    reinterpret_cast<float2*>(mr), n_per_group, 1.0 / count, eps);
         VPT_LAUNCH_CHECK();
         return VPT_OK;
     }
     const int wpb = 8;
     const long long blocks = (G + wpb - 1) / wpb;
-    stats_finalize_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
+    launch_k(stats_finalize_kernel, dim3((unsigned)blocks), dim3(wpb * 32), 0, (cudaStream_t)stream, 
         reinterpret_cast<const float2*>(stat_part), reinterpret_cast<float2*>(mr), G, n_per_group, 1.0 / count, eps);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
@@ -511,7 +520,7 @@ extern "C" int vpt_norm2_fold(const float* chan_part, int32_t NP, int32_t C, int
     using namespace vpt;
     VPT_CHECK(chan_part && gamma_n && beta_n && Ta && Tb && Tc && Td && mrE && Ef && res_scale && res_shift && F > 0, "vpt_norm2_fold: null argument");
     VPT_CHECK(C > 0 && C <= 512 && NP > 0 && Cout > 0, "vpt_norm2_fold: need 0 < C <= 512 (C=%d)", C);
-    norm2_fold_kernel<<<(unsigned)F, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(chan_part), NP, C, (double)npix, gamma_n, beta_n, Ta, Tb,
+    launch_k(norm2_fold_kernel, dim3((unsigned)F), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float2*>(chan_part), NP, C, (double)npix, gamma_n, beta_n, Ta, Tb,
                                                                     Tc, Td, Cout, eps, reinterpret_cast<float2*>(mrE), Ef, res_scale, res_shift);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
@@ -526,10 +535,10 @@ extern "C" int vpt_maxpool3s2(const void* in, void* out, float* stat_part, float
     VPT_CHECK(F <= 65535, "vpt_maxpool3s2: at most 65535 frames per call (got %d)", F);
     dim3 grid(chan_part ? vpt_pool_chan_parts(F, H, W, C) : vpt_pool_stat_parts(F, H, W, C), F);
     if (chan_part)
-        maxpool3s2_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
+        launch_k(maxpool3s2_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
                                                                       reinterpret_cast<float2*>(stat_part), reinterpret_cast<float2*>(chan_part), H, W, C / 8, zp ? 1 : 0);
     else
-        maxpool3s2_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
+        launch_k(maxpool3s2_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out),
                                                                        reinterpret_cast<float2*>(stat_part), nullptr, H, W, C / 8, zp ? 1 : 0);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
@@ -551,7 +560,7 @@ extern "C" int vpt_affine_norm(const void* in, const float* mr, const float* gam
     for (long long g0 = 0; g0 < G; g0 += 65535) {
         const long long gn = (G - g0 < 65535) ? (G - g0) : 65535;
         dim3 grid(bpg, (unsigned)gn);
-        affine_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        launch_k(affine_norm_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
             reinterpret_cast<const uint4*>(in) + g0 * items, reinterpret_cast<const float2*>(mr) + g0, gamma, beta,
             reinterpret_cast<uint4*>(out) + g0 * items, out_f32 ? out_f32 + g0 * items * 8 : nullptr,
             stat_part ? reinterpret_cast<float2*>(stat_part) + g0 * bpg : nullptr, items, C / 8);
@@ -572,11 +581,11 @@ extern "C" int vpt_affine_norm_zp(const void* in, const float* mr, const float* 
         const long long gn = (F - g0 < 65535) ? (F - g0) : 65535;
         dim3 grid(bpg, (unsigned)gn);
         if (fast)
-            affine_norm_zp_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            launch_k(affine_norm_zp_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
                 reinterpret_cast<const uint4*>(in) + g0 * items, reinterpret_cast<const float2*>(mr) + g0, gamma, beta,
                 reinterpret_cast<uint4*>(out) + g0 * items, stat_part ? reinterpret_cast<float2*>(stat_part) + g0 * bpg : nullptr, H, W, C / 8);
         else
-            affine_norm_zp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            launch_k(affine_norm_zp_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
                 reinterpret_cast<const uint4*>(in) + g0 * items, reinterpret_cast<const float2*>(mr) + g0, gamma, beta,
                 reinterpret_cast<uint4*>(out) + g0 * items, stat_part ? reinterpret_cast<float2*>(stat_part) + g0 * bpg : nullptr, H, W, C / 8);
         VPT_LAUNCH_CHECK();
@@ -606,7 +615,7 @@ extern "C" int vpt_copy_rows2(const void* src, const void* src2, int32_t src_f32
     dim3 grid(vpt_blocks_for((long long)rows * (cols / 8), 1024, 1024), B, src2 ? 2 : 1);
     cudaStream_t s = (cudaStream_t)stream;
 #define VPT_CR(SF, DF)                                                                                                                        \
-    copy_rows_kernel<SF, DF><<<grid, 256, 0, s>>>(src, src2, src_bstride, src_ld, src_off, dst, dst2, dst_bstride, dst_ld, dst_off, rows, \
+    launch_k(copy_rows_kernel<SF, DF>, dim3(grid), dim3(256), 0, s, src, src2, src_bstride, src_ld, src_off, dst, dst2, dst_bstride, dst_ld, dst_off, rows, \
                                                   cols / 8)
     if (src_f32 && dst_f32) VPT_CR(true, true);
     else if (src_f32) VPT_CR(true, false);
@@ -623,7 +632,7 @@ extern "C" int vpt_state_mask_update(const uint8_t* mask_in, const uint8_t* firs
     if (maxlen == 0 || B == 0) return VPT_OK;
     VPT_CHECK(first && mask_out && B > 0 && t > 0 && maxlen > 0, "vpt_state_mask_update: bad arguments");
     const int n = B * maxlen;
-    state_mask_update_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mask_in, first, first_stride, mask_out, B, t, maxlen);
+    launch_k(state_mask_update_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, mask_in, first, first_stride, mask_out, B, t, maxlen);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

@@ -29,6 +29,7 @@ constexpr int kFcPatchBytes = 2192;              // bf16 patch + one zero elemen
 __global__ void __launch_bounds__(kFcThreads, 2) firstconv_pool_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w,
                                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                                        float2* __restrict__ stat_part, int H, int W, int C0, long long total_tiles, int zp) {
+    pdl_sync();
     extern __shared__ __align__(16) uint8_t fc_smem[];
     __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(fc_smem);                                  // [19][19][3]
     __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(fc_smem + kFcPatchBytes);                     // [C0][72]
@@ -262,7 +263,7 @@ extern "C" int vpt_firstconv_pool(const uint8_t* img, const float* w, const floa
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)num_sms() * per_sm;
     if (grid > blocks) grid = blocks;
-    firstconv_pool_kernel<<<(unsigned)grid, kFcThreads, smem, (cudaStream_t)stream>>>(
+    launch_k(firstconv_pool_kernel, dim3((unsigned)grid), dim3(kFcThreads), smem, (cudaStream_t)stream, 
         img, w, bias, reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<float2*>(stat_part), H, W, C0, blocks, zp ? 1 : 0);
     VPT_LAUNCH_CHECK();
     return VPT_OK;

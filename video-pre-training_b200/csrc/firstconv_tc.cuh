@@ -163,6 +163,7 @@ __device__ __forceinline__ void ft_pool_chunk(const float (&a)[CW], const float 
 
 template <int W, bool F32OUT, bool BWD>
 __global__ void __launch_bounds__(kFtThreads, 1) firstconv_tc_kernel(const FirstconvTcParams p) {
+    pdl_sync();
     constexpr int NPOS = 2 * W;           // UMMA N: two conv rows
     constexpr int CW = 16;                // columns per epilogue chunk
     constexpr int NCH = W / 32;           // chunks per epilogue warp and conv row (the warp owns W/2 columns)
@@ -578,7 +579,7 @@ static int launch_firstconv_tc(const FirstconvTcParams& p0, void* stream, int fi
     long long grid = num_sms() > 0 ? num_sms() : 148;
     if (grid > p.items) grid = p.items;
     if (fixed_grid > 0) grid = fixed_grid;  // backward: the partial-sum workspace is sized for exactly this many CTAs
-    firstconv_tc_kernel<W, F32OUT, BWD><<<(unsigned)grid, kFtThreads, smem, (cudaStream_t)stream>>>(p);
+    launch_k(firstconv_tc_kernel<W, F32OUT, BWD>, dim3((unsigned)grid), dim3(kFtThreads), smem, (cudaStream_t)stream, p);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }

@@ -72,6 +72,7 @@ __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int num_sta
 template <bool kWgrad>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    pdl_sync();
     extern __shared__ uint8_t smem_raw[];
     // carve: [A stages][B stages][barriers]; operand tiles need 1024-byte alignment for SWIZZLE_128B
     const uint32_t raw = smem_u32(smem_raw);
@@ -615,7 +616,9 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (see pdl_sync() in common.cuh)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs;
     attr[0].val.clusterDim.y = 1;
@@ -637,6 +640,7 @@ extern "C" int vpt_gemm_bf16(const vpt_gemm_args* a, void* stream) {
     int clusters = max_clusters[cs];
     if (clusters > num_super) clusters = num_super;
     cfg.gridDim = dim3(clusters * cs);
+    cfg.numAttrs = g_pdl ? 2 : 1;
     VPT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, tmA, tmB, p));
     return VPT_OK;
 }

@@ -15,9 +15,18 @@ constexpr int kGsThreads = 256;
 
 constexpr int kGsUnroll = 8;  // 16-byte weight loads in flight per lane (8 x 512 B per warp: what it takes to cover HBM latency with few warps)
 
-__device__ __forceinline__ uint4 ld_stream16(const uint4* p) {  // read-once weights: do not displace the activations in L1
+// read-once weights: no L1 allocation, and evict-first in L2 -- the 0.5 GB weight stream of a rollout step would otherwise flush the
+// activations and the CNN weights (20 MB, re-read every step) out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_stream16(const uint4* p, uint64_t pol) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
     return v;
 }
 
@@ -26,9 +35,11 @@ __device__ __forceinline__ uint4 ld_stream16(const uint4* p) {  // read-once wei
 template <int kWpc>
 __global__ void __launch_bounds__(kGsThreads) gemv_small_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
                                                                   const GemmParams p) {
+    pdl_sync();
     __shared__ float s_part[kGsThreads / 32][kGsMaxM];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int M = p.M, K8 = p.K >> 3;
+    const uint64_t pol = l2_evict_first_policy();
     constexpr int kCols = (kGsThreads / 32) / kWpc;  // output columns per CTA
     const int kpart = warp % kWpc;
     const int chunk = ((K8 + kWpc - 1) / kWpc + 31) / 32 * 32;
@@ -43,7 +54,7 @@ __global__ void __launch_bounds__(kGsThreads) gemv_small_kernel(const __nv_bfloa
             for (int k0 = k_begin + lane; k0 < k_end; k0 += 32 * kGsUnroll) {
                 uint4 w[kGsUnroll];
 #pragma unroll
-                for (int u = 0; u < kGsUnroll; ++u) w[u] = (k0 + 32 * u < k_end) ? ld_stream16(wrow + k0 + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+                for (int u = 0; u < kGsUnroll; ++u) w[u] = (k0 + 32 * u < k_end) ? ld_stream16(wrow + k0 + 32 * u, pol) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int u = 0; u < kGsUnroll; ++u) {
                     const int k = k0 + 32 * u;
@@ -126,6 +137,7 @@ __global__ void __launch_bounds__(kGsThreads) gemv_small_kernel(const __nv_bfloa
 // statistics partials of the rows just stored, in the [M][P] layout of the tensor-core kernel: slot 0 carries the whole
 // row's (sum, sumsq), the other slots are zero.  One CTA per row (M <= 8, N <= a few thousand): negligible.
 __global__ void __launch_bounds__(256) row_stats_small_kernel(const GemmParams p, int P) {
+    pdl_sync();
     const int m = blockIdx.x;
     long long orow = m;
     if (p.seg_len > 0) orow = (long long)(m / p.seg_len) * p.seg_stride + p.seg_off + (m % p.seg_len);
@@ -167,14 +179,14 @@ static int try_launch_gemv_small(const vpt_gemm_args* a, void* stream) {
     int grid = split ? a->N : (a->N + kGsThreads / 32 - 1) / (kGsThreads / 32);
     if (grid > 8 * 148) grid = 8 * 148;
     if (split)
-        gemv_small_kernel<kGsThreads / 32><<<grid, kGsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->A),
+        launch_k(gemv_small_kernel<kGsThreads / 32>, dim3(grid), dim3(kGsThreads), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(a->A),
                                                                                           reinterpret_cast<const __nv_bfloat16*>(a->B), p);
     else
-        gemv_small_kernel<1><<<grid, kGsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(a->A),
+        launch_k(gemv_small_kernel<1>, dim3(grid), dim3(kGsThreads), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(a->A),
                                                                             reinterpret_cast<const __nv_bfloat16*>(a->B), p);
     VPT_LAUNCH_CHECK();
     if (a->stat_part) {
-        row_stats_small_kernel<<<a->M, 256, 0, (cudaStream_t)stream>>>(p, P);
+        launch_k(row_stats_small_kernel, dim3(a->M), dim3(256), 0, (cudaStream_t)stream, p, P);
         VPT_LAUNCH_CHECK();
     }
     return VPT_OK;

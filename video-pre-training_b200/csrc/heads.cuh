@@ -19,6 +19,7 @@ __device__ __forceinline__ float block_max(float v) {
 
 __global__ void __launch_bounds__(256) log_softmax_kernel(const float* __restrict__ in, long long ld_in, int col0, int n,
                                                             float* __restrict__ out) {
+    pdl_sync();
     __shared__ float bcast[2];
     const long long r = blockIdx.x;
     const float* x = in + r * ld_in + col0;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256) log_softmax_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) gumbel_argmax_kernel(const float* __restrict__ logits, const float* __restrict__ u,
                                                               long long* __restrict__ idx, int n) {
+    pdl_sync();
     __shared__ float bv[32];
     __shared__ int bi[32];
     const long long r = blockIdx.x;
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(256) gumbel_argmax_kernel(const float* __restr
 
 __global__ void gather_logprob_kernel(const float* __restrict__ logits, const long long* __restrict__ idx, float* __restrict__ lp,
                                       long long rows, int n, int accumulate) {
+    pdl_sync();
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const float v = logits[r * n + idx[r]];
@@ -106,7 +109,7 @@ __global__ void gather_logprob_kernel(const float* __restrict__ logits, const lo
 extern "C" int vpt_log_softmax(const float* in, int64_t ld_in, int32_t col0, int32_t n, float* out, int64_t rows, void* stream) {
     using namespace vpt;
     VPT_CHECK(in && out && rows > 0 && n > 0 && col0 >= 0, "vpt_log_softmax: bad arguments");
-    log_softmax_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(in, ld_in, col0, n, out);
+    launch_k(log_softmax_kernel, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, in, ld_in, col0, n, out);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
@@ -114,7 +117,7 @@ extern "C" int vpt_log_softmax(const float* in, int64_t ld_in, int32_t col0, int
 extern "C" int vpt_gumbel_argmax(const float* logits, const float* u, int64_t* idx, int64_t rows, int32_t n, void* stream) {
     using namespace vpt;
     VPT_CHECK(logits && idx && rows > 0 && n > 0, "vpt_gumbel_argmax: bad arguments");
-    gumbel_argmax_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(logits, u, reinterpret_cast<long long*>(idx), n);
+    launch_k(gumbel_argmax_kernel, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, logits, u, reinterpret_cast<long long*>(idx), n);
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
@@ -123,7 +126,7 @@ extern "C" int vpt_gather_logprob(const float* logits, const int64_t* idx, float
                                   void* stream) {
     using namespace vpt;
     VPT_CHECK(logits && idx && lp && rows > 0 && n > 0, "vpt_gather_logprob: bad arguments");
-    gather_logprob_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(gather_logprob_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         logits, reinterpret_cast<const long long*>(idx), lp, rows, n, accumulate);
     VPT_LAUNCH_CHECK();
     return VPT_OK;

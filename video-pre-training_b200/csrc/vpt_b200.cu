@@ -38,6 +38,10 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* vpt_last_error(void) { return vpt::g_err; }
 extern "C" int vpt_abi_version(void) { return VPT_ABI_VERSION; }
 extern "C" int vpt_num_sms(void) { return vpt::num_sms(); }
+extern "C" int vpt_set_pdl(int32_t on) {
+    vpt::g_pdl = on ? 1 : 0;
+    return VPT_OK;
+}
 extern "C" int vpt_device_error(void) {
     unsigned int v = 0;
     cudaError_t e = cudaDeviceSynchronize();

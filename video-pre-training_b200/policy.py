@@ -23,6 +23,7 @@ from typing import Dict, Optional
 import torch
 from torch import nn
 
+from . import _native as nat
 from . import ops
 from .types import DictType
 
@@ -826,10 +827,11 @@ class MinecraftAgentPolicy(_PolicyBase):
         ac = {k: v[:, 0] for k, v in ac.items()}
         return ac, state_out, result
 
-    def make_graphed_act(self, batch_size: int):
+    def make_graphed_act(self, batch_size: int, pdl: bool = False):
         """Rollout-latency path (agent.py:190-206, SURVEY f-1): returns a callable with the signature of `act` whose whole
-        step (forward + heads + sampling + log-prob + KV-memory roll) is ONE captured CUDA graph replay."""
-        return GraphedAct(self, batch_size)
+        step (forward + heads + sampling + log-prob + KV-memory roll) is ONE captured CUDA graph replay (pdl: captured with
+        programmatic dependent launch between its kernels -- bit-identical, and measured neutral on B200: 0.953 vs 0.957 ms/step)."""
+        return GraphedAct(self, batch_size, pdl=pdl)
 
     @torch.no_grad()
     def v(self, obs, first, state_in):
@@ -880,8 +882,9 @@ class GraphedAct:
     them (valid until the next call).  Passing any other state (e.g. `policy.initial_state(B)` after an episode reset)
     copies it in.  Sampling uses torch's graph-safe Philox generator, i.e. the same `rand_like` draws as eager mode."""
 
-    def __init__(self, policy: "MinecraftAgentPolicy", batch_size: int):
+    def __init__(self, policy: "MinecraftAgentPolicy", batch_size: int, pdl: bool = False):
         self.policy = policy
+        self.pdl = pdl
         cfg = policy.net.cfg
         dev = policy.net.final_ln.weight.device
         B, self.B = batch_size, batch_size
@@ -913,12 +916,18 @@ class GraphedAct:
 
     def _capture(self, stochastic: bool):
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            ac, st, res = self.policy.act({"img": self.img}, self.first, self.state, stochastic=stochastic, return_pd=True)
-            for (m_in, (k_in, v_in)), (m_out, (k_out, v_out)) in zip(self.state, st):  # roll the state inside the graph
-                m_in.copy_(m_out)
-                if k_in.shape[1] > 0:
-                    ops.copy_rows2(k_out, v_out, 0, k_in, v_in, 0, k_in.shape[1])  # K and V in one launch
+        # optional programmatic dependent launch: with the attribute the next kernel is scheduled while the previous one drains
+        # (csrc/common.cuh pdl_sync).  Measured neutral for this graph (0.953 vs 0.957 ms), hence off by default.
+        nat.lib().vpt_set_pdl(1 if self.pdl else 0)
+        try:
+            with torch.cuda.graph(g):
+                ac, st, res = self.policy.act({"img": self.img}, self.first, self.state, stochastic=stochastic, return_pd=True)
+                for (m_in, (k_in, v_in)), (m_out, (k_out, v_out)) in zip(self.state, st):  # roll the state inside the graph
+                    m_in.copy_(m_out)
+                    if k_in.shape[1] > 0:
+                        ops.copy_rows2(k_out, v_out, 0, k_in, v_in, 0, k_in.shape[1])  # K and V in one launch
+        finally:
+            nat.lib().vpt_set_pdl(0)
         self.graphs[stochastic] = (g, ac, res)
         return self.graphs[stochastic]
 
