@@ -1,5 +1,5 @@
 #!/bin/bash
 # One gpurun call = one batch of GPU work (this is the script the builder edits between calls; it travels with the repo snapshot).
 mkdir -p gpurun_out
-echo "=== policy tests"; timeout 1500 python -m pytest tests/test_gpu_policy.py tests/test_agent.py -x -q -m gpu 2>&1 | tail -8
-echo "=== rollout"; timeout 600 python tools/rollout_bench.py --steps 300 2>&1 | tail -8
+echo "=== kernel tests"; timeout 1500 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu 2>&1 | tail -5
+echo "=== pool bench"; timeout 600 python tools/pool_bench.py 2>&1 | tail -6

@@ -107,52 +107,65 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // partials of the pooled values -- what the two-norm composition (vpt_norm2_fold) needs instead of a normalisation pass.
 // (CHAN keeps 16 more accumulators: 48 registers -> 5 resident blocks instead of 8, and this kernel lives on loads in flight; two
 //  items per trip and a 4-block bound give each thread twice the loads instead -- measured in profiles/fold_r2.md)
+// One thread = one 8-channel group of a 2 x 2 block of outputs: the 5 x 5 input window is read once (6.25 loads per output instead of 9)
+// and the maximum is separable -- per input row two horizontal 3-maxima, folded into the two output rows that row belongs to.
 template <bool CHAN>
-__global__ void __launch_bounds__(256, CHAN ? 4 : 8) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+__global__ void __launch_bounds__(256, 2) maxpool3s2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                            float2* __restrict__ stat_part, float2* __restrict__ chan_part, int H, int W, int C8, int zp) {
     pdl_sync();
     const int Ho = H >> 1, Wo = W >> 1;
     const int ipitch = W + zp, opitch = Wo + zp;  // ZP layout: one extra zero column (and row) per frame
+    const int orows = Ho + zp;
+    const int nbx = (opitch + 1) >> 1, nby = (orows + 1) >> 1;
     const long long f = blockIdx.y;
-    const int items = (Ho + zp) * opitch * C8;
+    const int items = nby * nbx * C8;
     const uint4* fin = in + f * (long long)(H + zp) * ipitch * C8;
-    uint4* fout = out + f * (long long)items;
+    uint4* fout = out + f * (long long)orows * opitch * C8;
     float s = 0.f, ss = 0.f;
     float cs[8], css[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) cs[j] = css[j] = 0.f;
-#pragma unroll(CHAN ? 2 : 1)
+    auto max4 = [](uint4 a, const uint4 b) {
+        a.x = bf16x2_max(a.x, b.x); a.y = bf16x2_max(a.y, b.y); a.z = bf16x2_max(a.z, b.z); a.w = bf16x2_max(a.w, b.w);
+        return a;
+    };
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
-        const int c = i % C8, px = (i / C8) % opitch, py = i / (C8 * opitch);
-        uint4 m = make_uint4(0, 0, 0, 0);  // inputs are >= 0 (post-ReLU), so 0 == -inf padding
-        if (px >= Wo || py >= Ho) {  // zero column / row of the ZP output
-            fout[i] = m;
-            continue;
-        }
+        const int c = i % C8, bx = (i / C8) % nbx, by = i / (C8 * nbx);
+        const uint4 zero = make_uint4(0, 0, 0, 0);  // inputs are >= 0 (post-ReLU), so 0 == -inf padding
+        uint4 o[2][2] = {{zero, zero}, {zero, zero}};
+        const int x0 = 4 * bx - 1, y0 = 4 * by - 1;
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int y = 2 * py + dy;
+        for (int r = 0; r < 5; ++r) {
+            const int y = y0 + r;
             if (y < 0 || y >= H) continue;
+            const uint4* row = fin + ((long long)y * ipitch + x0) * C8 + c;
+            uint4 v[5];
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = 2 * px + dx;
-                if (x < 0 || x >= W) continue;
-                const uint4 v = __ldg(fin + ((long long)y * ipitch + x) * C8 + c);
-                m.x = bf16x2_max(m.x, v.x); m.y = bf16x2_max(m.y, v.y);
-                m.z = bf16x2_max(m.z, v.z); m.w = bf16x2_max(m.w, v.w);
-            }
+            for (int q = 0; q < 5; ++q) v[q] = (x0 + q >= 0 && x0 + q < W) ? __ldg(row + (long long)q * C8) : zero;
+            const uint4 h0 = max4(max4(v[0], v[1]), v[2]), h1 = max4(max4(v[2], v[3]), v[4]);
+            if (r <= 2) { o[0][0] = max4(o[0][0], h0); o[0][1] = max4(o[0][1], h1); }
+            if (r >= 2) { o[1][0] = max4(o[1][0], h0); o[1][1] = max4(o[1][1], h1); }
         }
-        fout[i] = m;
-        const uint32_t w4[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
-            if (CHAN) {  // per-channel sums; the frame sums are their total
-                cs[2 * q] += a; css[2 * q] = fmaf(a, a, css[2 * q]);
-                cs[2 * q + 1] += b; css[2 * q + 1] = fmaf(b, b, css[2 * q + 1]);
-            } else {
-                s += a + b;
-                ss = fmaf(a, a, fmaf(b, b, ss));
+        for (int ry = 0; ry < 2; ++ry) {
+#pragma unroll
+            for (int rx = 0; rx < 2; ++rx) {
+                const int oy = 2 * by + ry, ox = 2 * bx + rx;
+                if (oy >= orows || ox >= opitch) continue;
+                const uint4 m = (oy < Ho && ox < Wo) ? o[ry][rx] : zero;  // zero column / row of the ZP output
+                fout[((long long)oy * opitch + ox) * C8 + c] = m;
+                const uint32_t w4[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float a = bf16_lo(w4[q]), b = bf16_hi(w4[q]);
+                    if (CHAN) {  // per-channel sums; the frame sums are their total
+                        cs[2 * q] += a; css[2 * q] = fmaf(a, a, css[2 * q]);
+                        cs[2 * q + 1] += b; css[2 * q + 1] = fmaf(b, b, css[2 * q + 1]);
+                    } else {
+                        s += a + b;
+                        ss = fmaf(a, a, fmaf(b, b, ss));
+                    }
+                }
             }
         }
     }
