@@ -10,7 +10,7 @@ from video_pre_training_b200 import _native as nat, ops
 l = nat.lib()
 g = torch.Generator().manual_seed(0)
 shapes = [(64, 128, 128, 2048, False), (64, 128, 128, 2048, True)]
-variants = [("2phase", 1, 1), ("mma-only", 1, 2), ("frag", 1, 4), ("v3", 1, 5), ("v3 -class", 1, 0x200005)]
+variants = [("2phase 16w", 1, 1), ("2phase 8w", 1, 6), ("mma-only", 1, 2), ("2phase 16w", 1, 1), ("2phase 8w", 1, 6)]
 for (HW, Cin, N, F_, res) in shapes:
     x = torch.zeros(F_, HW + 1, HW + 1, Cin, dtype=torch.bfloat16, device="cuda")
     x[:, :HW, :HW] = torch.randn(F_, HW, HW, Cin, device="cuda").to(torch.bfloat16)

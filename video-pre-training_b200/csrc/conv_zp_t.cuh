@@ -44,6 +44,15 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
                  : "r"(taddr)
                  : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
@@ -80,8 +89,10 @@ __device__ __forceinline__ void v3_zero(float (&x)[32]) {
 
 // kFold (compile time, so that the plain variant's epilogue -- the co-bottleneck of this kernel -- is untouched by the extra code):
 // 0 = plain (S1 / S2 class tables), 1 = per-frame fold table Ef, 2 = plain fold + affine residual (two-norm composition, vpt_norm2_fold)
-template <int kFold>
-__global__ void __launch_bounds__(kCzThreads, 1)
+// kEw: epilogue warps (8 or 16).  The two-phase epilogue is bound by its dependent instruction chains, not by bandwidth (section 4 of DESIGN.md):
+// with 16 warps (4 per scheduler, <= 104 registers) each quarter-tile phase has half the work per thread and twice the latency hiding.
+template <int kFold, int kEw>
+__global__ void __launch_bounds__(96 + 32 * kEw, 1)
 conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
                     const __grid_constant__ CUtensorMap tmR, const ConvZpTParams p) {
     pdl_sync();
@@ -120,7 +131,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             mbar_init(&x_full[i], 1);
             mbar_init(&x_empty[i], 1);
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], kNumEpiWarps);
+            mbar_init(&tmem_empty_bar[i], kEw);
         }
         for (int i = 0; i < p.b_stages; ++i) {
             mbar_init(&w_full[i], 1);
@@ -209,7 +220,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (ok) umma_commit(&tmem_full_bar[as]);
             }
         }
-    } else if (p.epi_mode == 1) {
+    } else if (kEw == 8 && p.epi_mode == 1) {
         // ================= epilogue v2 (warps 3..10): fragments -> stmatrix.trans -> TMA store =================
         // Round-1 ncu on this kernel: tensor pipe 55-64 % active with the L1/shared pipe at 47 % -- the fp32 transposing store + the
         // row-major second pass cost ~3000 shared/L1 wavefronts per tile on the pipe the UMMA operand fetch needs.  Here the
@@ -368,7 +379,7 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
         }
         if (leader_t) bulk_wait_all<0>();
-    } else if (p.epi_mode == 2) {
+    } else if (kEw == 8 && p.epi_mode == 2) {
         // ================= epilogue v3 (warps 3..10): channel-major single pass -> bf16 staging -> TMA store =================
         // Thread = output channel (its TMEM lane), warp = 32 channels x one 128-pixel half.  Everything that depends on the PIXEL
         // (frame statistics, border class, zero row / column) is warp-uniform in this layout, so the fold is one FFMA per value with
@@ -609,11 +620,13 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         //   phase B (thread = pixel row x 32 channels): the regular epilogue -- fold with per-row constants and 16-byte table
         //           loads, ReLU, residual, bf16 rounding, statistics, 16-byte global stores.
         // Four 64-pixel quarters per tile keep the tile at 33 KB.
+        constexpr int kColsA = 256 / kEw;                  // phase A: pixel columns of a 64-pixel quarter per warp (32 or 16)
+        constexpr int kItemsB = 32 / kEw;                  // phase B: (row pair, 16 chunks) passes per warp and quarter (4 or 2)
         const int ew = warp - 3;
         const int quarter = warp & 3;
-        const int cgrp = ew >> 2;                          // phase A: which 32 of the quarter's 64 pixel columns
+        const int cgrp = ew >> 2;                          // phase A: which kColsA of the quarter's 64 pixel columns
         const int ch = quarter * 32 + lane;                // phase A: output channel of this thread
-        const int et = ew * 32 + lane;                     // 0..255
+        const int et = ew * 32 + lane;                     // 0..32 kEw - 1
         int local = 0;
         bool ok = true;
         for (long long tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++local) {
@@ -667,20 +680,20 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 s_info0[(hh & 1) * 64 + et] = info;
             };
             if (local == 0) write_info(tile, 0);  // later tiles: written during the previous tile's last quarter
-            uint4 rres_n[4];
+            uint4 rres_n[kItemsB];
             auto prefetch_res = [&](int hh) {
                 if (!p.residual) return;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const long long q = q0 + hh * 64 + 2 * (ew * 4 + i) + (lane & 1);
+                for (int i = 0; i < kItemsB; ++i) {
+                    const long long q = q0 + hh * 64 + 2 * (ew * kItemsB + i) + (lane & 1);
                     if (q < p.Q) rres_n[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)q * 128 + c0));
                 }
             };
             prefetch_res(0);
             for (int h = 0; h < 4; ++h) {
-                uint4 rres[4];
+                uint4 rres[kItemsB];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) rres[i] = rres_n[i];
+                for (int i = 0; i < kItemsB; ++i) rres[i] = rres_n[i];
                 if (h < 3) prefetch_res(h + 1);
                 // the transposed tile and the row-info table are double buffered (quarter h uses buffer h & 1): the single
                 // barrier below orders A(h) -> B(h) and, because every warp reaches it only after its own B(h - 1), also
@@ -688,26 +701,28 @@ conv3x3_zp_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 float* s_tile = s_tile0 + (h & 1) * (64 * kCtPitch);
                 float4* s_info = s_info0 + (h & 1) * 64;
                 if (p.dbg_skip_epilogue != 2) {  // ---- phase A: TMEM -> transposed fp32 tile
-                    uint32_t acc[32];
-                    const int pl0 = cgrp * 32;
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + h * 64 + pl0), acc);
+                    uint32_t acc[kColsA];
+                    const int pl0 = cgrp * kColsA;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccStageCols + h * 64 + pl0);
+                    if constexpr (kColsA == 32) tmem_ld_32x32(taddr, acc);
+                    else tmem_ld_32x16(taddr, acc);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) s_tile[(pl0 + j) * kCtPitch + ch] = __uint_as_float(acc[j]);
+                    for (int j = 0; j < kColsA; ++j) s_tile[(pl0 + j) * kCtPitch + ch] = __uint_as_float(acc[j]);
                 }
                 if (h == 3) {  // TMEM fully drained: release the accumulator stage to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                named_bar_sync(1, 32 * kEw);
                 if (h < 3) write_info(tile, h + 1);
                 else write_info(tile + gridDim.x, 0);
                 if (p.dbg_skip_epilogue == 2) continue;
                 // ---- phase B
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int prow = 2 * (ew * 4 + i) + (lane & 1);
+                for (int i = 0; i < kItemsB; ++i) {
+                    const int prow = 2 * (ew * kItemsB + i) + (lane & 1);
                     const long long q = q0 + h * 64 + prow;
                     const float4 info = s_info[prow];
                     const int cls = (int)info.z;
@@ -870,18 +885,31 @@ static int launch_conv_zp_t(const vpt_conv_zp_args* a, void* stream) {
     p.dbg_skip_epilogue = (swap_mode == 2) ? 2 : (dbg_bits & 0xf0);  // v3 experiment bits: 16 no STS, 32 no classification, 64 no TMA store, 128 no LDTM  // 2: no epilogue work (MMA-rate experiment)
     static bool attr_set = false;
     if (!attr_set) {
-        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        VPT_CUDA(cudaFuncSetAttribute(conv3x3_zp_t_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     long long grid = num_sms();
     if (grid <= 0) grid = 148;
     if (grid > p.num_tiles) grid = p.num_tiles;
     VPT_CHECK(!(a->Ef && a->res_scale), "vpt_conv3x3_zp: Ef and res_scale are not combined (Cout == 128 kernel)");
-    if (a->Ef) launch_k(conv3x3_zp_t_kernel<1>, dim3((unsigned)grid), dim3(kCzThreads), smem_bytes, (cudaStream_t)stream, tmX, tmW, tmO, tmR, p);
-    else if (a->res_scale) launch_k(conv3x3_zp_t_kernel<2>, dim3((unsigned)grid), dim3(kCzThreads), smem_bytes, (cudaStream_t)stream, tmX, tmW, tmO, tmR, p);
-    else launch_k(conv3x3_zp_t_kernel<0>, dim3((unsigned)grid), dim3(kCzThreads), smem_bytes, (cudaStream_t)stream, tmX, tmW, tmO, tmR, p);
+    // 16 epilogue warps for the two-phase epilogue (swap mode 1); swap mode 6 = the same with 8 warps (A-B), the experiments (4, 5) are written for 8
+    const bool ew16 = p.epi_mode == 0 && swap_mode != 6 && swap_mode != 2;
+    const dim3 g((unsigned)grid), b8(96 + 32 * 8), b16(96 + 32 * 16);
+    const cudaStream_t st = (cudaStream_t)stream;
+    if (ew16) {
+        if (a->Ef) launch_k(conv3x3_zp_t_kernel<1, 16>, g, b16, smem_bytes, st, tmX, tmW, tmO, tmR, p);
+        else if (a->res_scale) launch_k(conv3x3_zp_t_kernel<2, 16>, g, b16, smem_bytes, st, tmX, tmW, tmO, tmR, p);
+        else launch_k(conv3x3_zp_t_kernel<0, 16>, g, b16, smem_bytes, st, tmX, tmW, tmO, tmR, p);
+    } else {
+        if (a->Ef) launch_k(conv3x3_zp_t_kernel<1, 8>, g, b8, smem_bytes, st, tmX, tmW, tmO, tmR, p);
+        else if (a->res_scale) launch_k(conv3x3_zp_t_kernel<2, 8>, g, b8, smem_bytes, st, tmX, tmW, tmO, tmR, p);
+        else launch_k(conv3x3_zp_t_kernel<0, 8>, g, b8, smem_bytes, st, tmX, tmW, tmO, tmR, p);
+    }
     VPT_LAUNCH_CHECK();
     return VPT_OK;
 }
