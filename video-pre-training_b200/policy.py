@@ -779,10 +779,16 @@ class MinecraftAgentPolicy(_PolicyBase):
     def denormalize(self, v):
         """lib/normalize_ewma.py:31-35,57-60 (a 3-scalar affine map; host-side glue)."""
         nz = self.value_head.normalizer
-        deb = nz.debiasing_term.clamp(min=1e-5)
-        mean = nz.running_mean / deb
-        var = (nz.running_mean_sq / deb - mean ** 2).clamp(min=1e-2)
-        return v * torch.sqrt(var)[None, None] + mean[None, None]
+        bufs = (nz.debiasing_term, nz.running_mean, nz.running_mean_sq)
+        key = tuple((b.data_ptr(), b._version) for b in bufs)
+        if getattr(self, "_denorm_key", None) != key:  # the three scalars only change when the normaliser is updated / reloaded:
+            deb = nz.debiasing_term.clamp(min=1e-5)    # 7 of the 9 tiny launches per rollout step were this recomputation
+            mean = nz.running_mean / deb
+            var = (nz.running_mean_sq / deb - mean ** 2).clamp(min=1e-2)
+            self._denorm = (torch.sqrt(var)[None, None], mean[None, None])
+            self._denorm_key = key
+        std, mean = self._denorm
+        return v * std + mean
 
     def get_logprob_of_action(self, pd, action):
         """lib/policy.py:271-279."""
@@ -913,6 +919,9 @@ class GraphedAct:
         which parameter versions they were made from (a later load_weights / optimizer step invalidates the graph)."""
         self._fp = self._weights_fp()
         self._held = (self.policy.net.prepared(), self.policy._heads_prepared())
+        if self.policy.has_value_head:  # refresh the cached de-normalisation scalars OUTSIDE the capture (they must not live in the graph's pool)
+            with torch.no_grad():
+                self.policy.denormalize(torch.zeros((1, 1, 1), device=self.img.device))
 
     def _capture(self, stochastic: bool):
         g = torch.cuda.CUDAGraph()
