@@ -550,6 +550,7 @@ int launch_conv_zp_t_fwd(const vpt_conv_zp_args* a, void* stream);
 namespace vpt {
 // Weight-tile width.  A handful of frames (rollout: F = 1, 1089 rows at 32 x 32): the launch is a read of the 1.2 MB weight tensor through
 // the few SMs that have a tile, so narrower weight tiles put more SMs (each fetching a slice) on it -- ~64 CTAs instead of 5.
+static inline bool conv_zp_use_swapped(long long Q) { return (Q + 255) / 256 >= 32; }
 static inline void conv_zp_block_n(long long Q, int N, int* bn, int* nt) {
     choose_block_n(N, bn, nt);
     const long long tiles = (Q + 255) / 256;
@@ -569,7 +570,9 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
               "vpt_conv3x3_zp: need F>0, H,W>=2, Cin %% 64 == 0, Cout %% 16 == 0 (F=%d H=%d W=%d Cin=%d Cout=%d)", a->F, H, W, C, N);
     VPT_CHECK(W + 1 <= 255, "vpt_conv3x3_zp: W=%d too wide for one shared-memory span", W);
     VPT_CHECK(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->w & 15) == 0 && ((uintptr_t)a->out & 15) == 0, "vpt_conv3x3_zp: pointers must be 16-byte aligned");
-    if (N == 128 && g_cz_swap_enabled()) return launch_conv_zp_t_fwd(a, stream);  // operand-swapped kernel (conv_zp_t.cuh)
+    // operand-swapped kernel (conv_zp_t.cuh) for Cout == 128 -- except for a handful of frames: a 256-pixel tile is a serial chain of 72 UMMAs
+    // of ~204 cycles on 17 SMs, 128-row tiles with 32-channel weight slices are 72 UMMAs of ~92 cycles on 136
+    if (N == 128 && g_cz_swap_enabled() && conv_zp_use_swapped((long long)a->F * (H + 1) * (W + 1))) return launch_conv_zp_t_fwd(a, stream);
     ConvZpParams p;
     memset(&p, 0, sizeof(p));
     p.H = H; p.W = W; p.Wp = W + 1; p.FS = (H + 1) * (W + 1);
@@ -580,7 +583,9 @@ extern "C" int vpt_conv3x3_zp(const vpt_conv_zp_args* a, void* stream) {
     // measured (tools/conv_bench.py): SM pairs win for 256-wide weight tiles (+11-13 %), a single CTA with two 128-row
     // sub-tiles wins for <= 128 output channels; g_cz_pair: 0 = never, 1 = auto, 2 = always
     const bool pair = (g_cz_pair == 2 || (g_cz_pair == 1 && p.block_n > 128)) && (p.block_n % 16 == 0) && (p.Q > 256);
-    p.mt = (!pair && p.block_n <= 128) ? 2 : 1;
+    // two 128-row sub-tiles per CTA amortise the weight tile -- unless the launch is tiny (single frame): then the tile's UMMA chain IS the
+    // launch time (144 instructions of >= 84 cycles at K = 2304), and one sub-tile per CTA halves it
+    p.mt = (!pair && p.block_n <= 128 && (p.Q + 255) / 256 >= 32) ? 2 : 1;
     const int cta_rows = p.mt * kBlockM;                  // rows per CTA per tile
     const int tile_rows = cta_rows * (pair ? 2 : 1);
     p.num_m_tiles = (p.Q + tile_rows - 1) / tile_rows;
@@ -697,8 +702,9 @@ extern "C" int vpt_set_conv_pair_mode(int32_t on) {
 }
 
 extern "C" int vpt_conv_zp_stat_parts(int32_t F, int32_t H, int32_t W, int32_t Cout) {
-    if (Cout == 128 && vpt::g_cz_swap_enabled()) return 1;  // swapped kernel, round-1 epilogue: complete row sums (see vpt_conv_zp_t_stat_floats)
+    const long long Q = (long long)F * (H + 1) * (W + 1);
+    if (Cout == 128 && vpt::g_cz_swap_enabled() && vpt::conv_zp_use_swapped(Q)) return 1;  // swapped kernel: complete row sums (see vpt_conv_zp_t_stat_floats)
     int bn, nt;
-    vpt::conv_zp_block_n((long long)F * (H + 1) * (W + 1), Cout, &bn, &nt);
+    vpt::conv_zp_block_n(Q, Cout, &bn, &nt);
     return nt * 2;
 }

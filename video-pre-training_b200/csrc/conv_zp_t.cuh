@@ -959,6 +959,7 @@ extern "C" int vpt_set_conv_swap_mode(int32_t on) {
  * slots] float2), 0 when another kernel / epilogue handles this shape (then vpt_conv_zp_stat_parts + vpt_stats_finalize apply). */
 extern "C" int64_t vpt_conv_zp_t_stat_floats(int32_t F, int32_t H, int32_t W, int32_t Cout) {
     const int mode = vpt::g_cz_swap & 0xff;
+    if (!vpt::conv_zp_use_swapped((long long)F * (H + 1) * (W + 1))) return 0;
     if (Cout != 128 || (mode != 4 && mode != 5) || (H + 1) * (W + 1) < vpt::kCtPix || (mode == 5 && (W < 33 || H < 8))) return 0;
     const long long Q = (long long)F * (H + 1) * (W + 1);
     return ((Q + vpt::kCtPix - 1) / vpt::kCtPix) * 8 * 2 * 2;
