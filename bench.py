@@ -456,7 +456,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on STDOUT when the communicator is created (eagerly here: device_id is given); the contract is ONE
+        # JSON line on stdout, so file descriptor 1 points at stderr for the duration of the initialisation
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B, T = args.batch, args.timesteps
     kw = vpt_b200.policy_kwargs(args.width)
     torch.manual_seed(0)
