@@ -168,6 +168,19 @@ def test_full_size_chunk_2x_rows_match_oracle_and_are_batch_independent():
                 assert e < RTOL_BF16, (ci, k, e)
 
 
+def test_rollout_shape_2x_matches_oracle():
+    """The rollout shape (2x width, B = 1 and 2, T = 1, several steps with the KV memory filling up) against the oracle: single-frame
+    launches take their own code paths (128-row conv tiles with 32-channel weight slices, the regular kernel instead of the swapped one
+    for Cout = 128, frame-aware pool blocks, the weight-streaming GEMV with its K split for `dense`)."""
+    kw = vpt_b200.policy_kwargs("2x")
+    pol, sd, cfg = make_policy(kw, pert=True, seed=8)
+    pol = pol.to(DEV)
+    for B in (1, 2):
+        res = run_chunks(pol, sd, cfg, B=B, chunks=[1, 1, 1, 1], dev=DEV, first_at=(2, 0), seed=31 + B)
+        nat.device_check()
+        _check(res, f"rollout 2x B={B}")
+
+
 def test_graphed_act_matches_eager_and_logit_mask():
     """Rollout path (SURVEY f-1): one CUDA-graph replay per step == the eager act(); plus the obs["mask"] side input."""
     pol, sd, cfg = make_policy(small_kwargs())
