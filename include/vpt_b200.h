@@ -136,8 +136,10 @@ int vpt_conv3x3_zp(const vpt_conv_zp_args* args, void* stream);
 /* SM pairs cooperating on 256-row tiles with tcgen05.mma.cta_group::2 (each CTA stages half of the weight tile):
  * 0 = never, 1 = auto (default: pairs when Cout > 128, where they measure +11-13 %), 2 = always.  Tuning / A-B knob. */
 int vpt_set_conv_pair_mode(int32_t on);
-/* 1 (default): Cout == 128 layers run the operand-swapped kernel (channels as UMMA M, 256 pixels as N; see
- * csrc/conv_zp_t.cuh); 0: the regular orientation.  Changes vpt_conv_zp_stat_parts(128).  Tuning / A-B knob. */
+/* 1 (default): Cout == 128 layers (of launches with >= 32 tiles) run the operand-swapped kernel (channels as UMMA M, 256 pixels as N; see
+ * csrc/conv_zp_t.cuh) with its two-phase epilogue on 16 warps; 0: the regular orientation; 6: the two-phase epilogue on 8 warps; 2 / 4 / 5:
+ * timing experiment without an epilogue / fragment epilogue / channel-major single-pass epilogue.  Changes
+ * vpt_conv_zp_stat_parts(.., 128) and vpt_conv_zp_t_stat_floats.  Tuning / A-B knob: results are identical up to fp32 summation order of the statistics. */
 int vpt_set_conv_swap_mode(int32_t on);
 int vpt_conv_zp_stat_parts(int32_t F, int32_t H, int32_t W, int32_t Cout);  /* (few frames use narrower weight tiles, hence more partials per row) */
 /* Cout == 128 with the operand-swapped kernel's experimental fragment epilogue (vpt_set_conv_swap_mode(4)): its statistics partials are per (tile, warp, frame slot),

@@ -1,5 +1,5 @@
 """Micro-benchmark of vpt_conv3x3_zp on the stack-0 layer shape (128 -> 128 @ 64x64): A/B of the Cout == 128 kernel's epilogue variants.
-  swap mode 1 = two-phase transposing epilogue (default), 2 = no epilogue (MMA-rate experiment), 4 = fragment epilogue, 5 = channel-major
+  swap mode 1 = two-phase transposing epilogue on 16 warps (default), 6 = the same on 8 warps, 2 = no epilogue (MMA-rate experiment), 4 = fragment epilogue, 5 = channel-major
   single-pass epilogue (v3); bits 8..15 cap the weight pipeline depth, bits 20..23 switch parts of v3 off (timing experiments only).
   pair mode bit 8 (0x100) = round-1 per-thread global-store epilogue instead of the TMA-store one (pair kernel)."""
 import os, sys
@@ -10,7 +10,7 @@ from video_pre_training_b200 import _native as nat, ops
 l = nat.lib()
 g = torch.Generator().manual_seed(0)
 shapes = [(64, 128, 128, 2048, False), (64, 128, 128, 2048, True)]
-variants = [("2phase 16w", 1, 1), ("2phase 8w", 1, 6), ("mma-only", 1, 2), ("2phase 16w", 1, 1), ("2phase 8w", 1, 6)]
+variants = [("2phase 16w", 1, 1), ("2phase 8w", 1, 6), ("mma-only", 1, 2), ("frag", 1, 4), ("v3", 1, 5)]
 for (HW, Cin, N, F_, res) in shapes:
     x = torch.zeros(F_, HW + 1, HW + 1, Cin, dtype=torch.bfloat16, device="cuda")
     x[:, :HW, :HW] = torch.randn(F_, HW, HW, Cin, device="cuda").to(torch.bfloat16)
